@@ -1,0 +1,201 @@
+/*
+ * traceweaver_b200.h — C ABI of the B200-native span-assignment engine.
+ *
+ * Drop-in scope: ONE path of Sachin-A/TraceWeaver — `TraceWeaverV3.FindAssignments` for
+ * method "MaxScoreBatchSubsetWithSkips" (reference
+ * src/trace_reconstructor/ports/python/algorithms/traceweaver_v3.py:1087-1229, called from
+ * executor.py:1172-1175).  The reference has no FFI of its own (it is single-process Python, its
+ * C++ "port" is an empty skeleton — ports/cpp/scheme.cpp:8-10), so the entry points below are
+ * what a ctypes binding placed inside `TraceWeaverV3.FindAssignments` would call; INTEGRATION.md
+ * shows that stub.  Every entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types in any signature; all buffers are caller-owned.
+ *   - every pointer inside tw_batch / tw_params / tw_pass_out is a DEVICE pointer unless the
+ *     field comment says "host".  `stream` is a cudaStream_t passed as void*.
+ *   - every function returns TW_OK (0) or a negative tw_status; nothing throws across the ABI.
+ *   - times are int64 microseconds (Jaeger startTime is ~1.7e15 us: differences are formed in
+ *     int64 BEFORE conversion to double); scores are IEEE double.
+ *   - "problem" = one service: one incoming endpoint with n_in spans and E outgoing endpoints
+ *     ("eps") in the topological order of the invocation graph (traceweaver_v1.py:37-39).
+ *     In-spans and each ep's out-spans are sorted by (start, end) (executor.py:1111-1112).
+ *     A batch concatenates many problems so one launch sequence covers all of them.
+ */
+#ifndef TRACEWEAVER_B200_H
+#define TRACEWEAVER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TW_ABI_VERSION 1
+
+/* Algorithm constants hard-coded by the reference. */
+#define TW_MAX_E 8             /* engine limit on out-eps per service (shipped data: <= 4)      */
+#define TW_K 5                 /* topK                    traceweaver_v3.py:1109                */
+#define TW_MAX_WINDOW 30       /* batch_size_mis          traceweaver_v3.py:1108                */
+#define TW_WINDOW_CAP 31       /* a window opened by a perfect cut can reach 31 (v3:1063-1072) */
+#define TW_PARAM_BATCH 100     /* batch_size              traceweaver_v3.py:1107                */
+#define TW_PARAM_NBATCHES 10   /* nbatches                traceweaver_v3.py:599                 */
+#define TW_WEIGHT_OFFSET 10000.0 /* MWIS vertex weight    traceweaver_v3.py:1260                */
+#define TW_GMM_MAX_COMP 5      /* max mixture components  traceweaver_v3.py:768                 */
+#define TW_GAUSS_REC 3         /* doubles per pass-0 record: mu, sigma, log(sigma)              */
+#define TW_MIX_REC 21          /* doubles per mixture record: k, pc[5], mu*pc[5], logdet[5], logw[5] */
+
+typedef enum tw_status {
+  TW_OK = 0,
+  TW_ERR_INVALID = -1,        /* malformed descriptor (E > TW_MAX_E, empty problem, bad offsets) */
+  TW_ERR_CUDA = -2,           /* a CUDA runtime call failed; see tw_last_error()                 */
+  TW_ERR_MWIS_LIMIT = -3,     /* exact MWIS branch-and-bound exceeded its node budget            */
+  TW_ERR_RANGE_LIMIT = -4,    /* an in-span has more candidates per ep than the engine supports  */
+  TW_ERR_UNSUPPORTED = -5,    /* skip budgets != 0 (n_out != n_in): SURVEY.md §8 row f-4, not built */
+  TW_ERR_NO_DEVICE = -6       /* no CUDA device / wrong architecture                              */
+} tw_status;
+
+/* Term kinds of the score (traceweaver_v1.py:316-357). */
+#define TW_TERM_ROOT (-1)      /* l(c_e.start - in.start | in_ep, e)   when ep e has no in-edges  */
+#define TW_TERM_LAST (-2)      /* l(in.end - c_e.end | e, in_ep)       for the ep whose span ends last */
+
+/*
+ * A batch of problems, SoA.  Host code builds the (small) descriptor arrays; span arrays are the
+ * bulk data.  Replaces the `{ep: [Span]}` partitions + nx.DiGraph passed at executor.py:1172-1175.
+ */
+typedef struct tw_batch {
+  int32_t n_problems;            /* P                                                             */
+  int32_t n_ep_total;            /* sum over problems of E                                        */
+  int32_t n_term_total;          /* sum over problems of score terms                              */
+  int32_t reserved0;
+  int64_t n_in_total;
+  int64_t n_out_total;
+  const int64_t* prob_in_off;    /* [P+1]  in-span offset of problem p                            */
+  const int32_t* prob_ep_off;    /* [P+1]  first global ep index of problem p (E = difference)    */
+  const int64_t* prob_tuple_off; /* [P+1]  cumulative n_in*E: base of per-(ep,in-span) outputs    */
+  const int64_t* ep_out_off;     /* [n_ep_total+1] out-span offset of (problem, ep)               */
+  const int32_t* ep_term_off;    /* [n_ep_total+1] first global term index of (problem, ep).
+                                    Terms of ep e, in the reference's summation order
+                                    (traceweaver_v1.py:316-357): one per PRIMARY in-edge b->e in
+                                    in_edges order, else one ROOT term if e has no in-edges; then
+                                    always the LAST term.                                          */
+  const uint32_t* ep_pred_mask;  /* [n_ep_total] bit b set: DAG edge (topo position b) -> e; every
+                                    edge, primary or not, is a feasibility constraint
+                                    (traceweaver_v3.py:335-347)                                    */
+  const int8_t* term_src;        /* [n_term_total] b >= 0: edge term from topo position b;
+                                    TW_TERM_ROOT / TW_TERM_LAST                                    */
+  const int64_t* in_start;       /* [n_in_total]                                                  */
+  const int64_t* in_end;         /* [n_in_total]  start_mus + duration_mus                        */
+  const int64_t* out_start;      /* [n_out_total]                                                 */
+  const int64_t* out_end;        /* [n_out_total]                                                 */
+} tw_batch;
+
+/* Delay-distribution parameters for one pass (replaces self.services_times, traceweaver_v1.py:118). */
+#define TW_PARAMS_GAUSS_BATCHED 0 /* pass 0: one (mu, sigma) per term per 100-in-span batch (v3:1173-1178) */
+#define TW_PARAMS_MIXTURE 1       /* pass 1: one GMM (or degenerate Gaussian) per term (v3:1221-1222)      */
+typedef struct tw_params {
+  int32_t mode;
+  int32_t reserved0;
+  const int64_t* prob_gauss_off; /* [P+1] record offset of problem p's [n_batches][n_terms] table   */
+  const double* gauss;           /* TW_GAUSS_REC doubles per record                                 */
+  const double* mix;             /* [n_term_total][TW_MIX_REC]; k = 0 means Gaussian in pc[0..2]    */
+} tw_params;
+
+/* Per-pass results (replaces the 6-tuple of traceweaver_v3.py:1229 before id translation). */
+typedef struct tw_pass_out {
+  int32_t* assign;        /* [prob_tuple_off[P]]  assign[tuple_off[p] + e*n_in_p + i] = index into ep
+                             e's out list, -1 = ("NA","NA")                  (v1:433-455)         */
+  int8_t* mis_rank;       /* [n_in_total] rank of the chosen candidate in top_k, -1 = none        */
+  int32_t* n_cand;        /* [n_in_total] feasible tuples seen by the with-deletion search
+                             (per_span_candidates, v3:174-178)                                    */
+  double* topk_score;     /* [n_in_total][K]  with-deletion top-K (v3:1182); NaN padded; may be NULL */
+  int32_t* topk_idx;      /* [K * prob_tuple_off[P]]  idx[K*(tuple_off[p] + i*E) + r*E + e]; may be NULL */
+  uint8_t* topk_cnt;      /* [n_in_total] valid ranks; may be NULL                               */
+  int32_t* counters;      /* [P][4]: not_best_count, cnt_unassigned, mwis_nodes_max, status       */
+} tw_pass_out;
+
+/* No-deletion scoring results (top_k_2, v3:1185 -> all_topk_assignments) and window cuts. */
+typedef struct tw_score_out {
+  double* topk_score;     /* [n_in_total][K] descending, NaN padded; NULL = windows only          */
+  int32_t* topk_idx;      /* same layout as tw_pass_out.topk_idx                                   */
+  uint8_t* topk_cnt;      /* [n_in_total]                                                         */
+  int32_t* n_feasible;    /* [n_in_total] number of feasible tuples on the undeleted lists         */
+  uint8_t* cut;           /* [n_in_total] 1 iff PerfectCut(i) (v3:1024-1039); cut[first]=0         */
+} tw_score_out;
+
+typedef struct tw_engine tw_engine;   /* opaque: device scratch, CUDA graph cache, error string  */
+
+/* Library / device probing. */
+int tw_abi_version(void);
+const char* tw_last_error(void);
+int tw_device_count(void);
+
+/* Engine lifetime.  `device` is a CUDA ordinal; scratch grows on demand and is reused. */
+int tw_engine_create(int device, tw_engine** out);
+int tw_engine_destroy(tw_engine* eng);
+
+/* Host-side validation of descriptor arrays given as HOST pointers (same struct, host copies of
+ * the small arrays; span arrays may be NULL).  Mirrors the asserts at v3:1088,1198. */
+int tw_batch_validate_host(const tw_batch* host_desc);
+
+/*
+ * Pass-0 parameters on the device: order-statistics mean/std per term per 100-in-span batch.
+ * Replaces ComputeEpPairDistParams3 (traceweaver_v3.py:580-646) incl. scipy.stats.tstd.
+ * Writes prob_gauss_off[P]-addressed records into `gauss_out`.
+ */
+int tw_params_pass0(tw_engine* eng, const tw_batch* b, const int64_t* prob_gauss_off,
+                    double* gauss_out, void* stream);
+
+/*
+ * Candidate enumeration + scoring + top-K on the UNDELETED lists, plus perfect-cut flags.
+ * Replaces FindTopKAssignments(K=5, out_span_partitions) (v3:1185, :180-465 with DfsTraverseX
+ * :292-351 and ScoreAssignmentAsPerInvocationGraph v1:259-361 / GetEpPairCost v1:117-139) and
+ * the pre-processing half of CreateWindows2 (v3:1041-1051 + PerfectCut :1024-1039).
+ * `params` may be NULL: windows only (no scoring).
+ */
+int tw_score_topk(tw_engine* eng, const tw_batch* b, const tw_params* params,
+                  const tw_score_out* out, void* stream);
+
+/*
+ * The sequential part of one pass: windows from cut flags (v3:1056-1076), per in-span top-K on
+ * the not-yet-taken out spans (v3:1182), exact MWIS per window (BuildMISInstance v3:1252-1274 +
+ * gurobi_optimods.mwis at v3:1411), assignment + deletion (AddAssignment v1:433-463).
+ */
+int tw_stitch(tw_engine* eng, const tw_batch* b, const tw_params* params,
+              const uint8_t* cut, const tw_pass_out* out, void* stream);
+
+/*
+ * Delay samples implied by a pass's assignments, per term (ComputeEpPairDistParams5's
+ * `durations`, traceweaver_v3.py:721-760).  delays[term_sample_off[t] + j]; NA rows are dropped
+ * and counts[t] receives the number of samples.  Sample capacity of term t of problem p = n_in_p.
+ */
+int tw_delays(tw_engine* eng, const tw_batch* b, const int32_t* assign,
+              const int64_t* term_sample_off, double* delays, int32_t* counts, void* stream);
+
+/*
+ * Pass-boundary refit on the device: per term, 1-D Gaussian mixtures with 1..min(5,#unique)
+ * components, BIC model selection, final full-covariance fit — the algorithm of
+ * sklearn.mixture.GaussianMixture as called at traceweaver_v3.py:768-786 (k-means++ / Lloyd
+ * initialisation, EM with tol 1e-3, reg_covar 1e-6, max_iter 100).  Writes TW_MIX_REC records.
+ * `seed_select` seeds the model-selection fits (the reference leaves them to the unseeded global
+ * NumPy RNG, v3:774), the final fit uses seed 100 (v3:784).
+ */
+int tw_gmm_refit(tw_engine* eng, int32_t n_terms, const int64_t* term_sample_off,
+                 const double* delays, const int32_t* counts, uint32_t seed_select,
+                 double* mix_out, int32_t* n_selected_out, void* stream);
+
+/*
+ * Whole path, both passes, for a batch whose span arrays are already on the device:
+ * params0 -> score (windows) -> stitch -> delays -> refit -> score (final top-K) -> stitch.
+ * = TraceWeaverV3.FindAssignments v3:1087-1229 for every problem of the batch.
+ * `final` receives the last pass; `topk_final` the no-deletion top-K of the last pass
+ * (all_topk_assignments); n_cand_total[i] sums both passes (per_span_candidates is not reset
+ * between iterations, v3:1093 vs :1159).
+ */
+int tw_find_assignments(tw_engine* eng, const tw_batch* b, uint32_t seed_select,
+                        const tw_pass_out* final, const tw_score_out* topk_final,
+                        int32_t* n_cand_total, double* mix_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRACEWEAVER_B200_H */

@@ -1,0 +1,177 @@
+// tw_emul.cpp — CPU stepping of the engine's per-thread device functions (tw_core.cuh).
+//
+// TEST INFRASTRUCTURE ONLY.  The build container has no GPU; this file compiles the very same
+// __host__ __device__ functions the CUDA kernels call (enumerate, score_tuple, topk_offer,
+// bitmaps_intersect, WindowCursor, mwis_solve) with g++ and walks the kernels' thread/warp loops
+// sequentially, so logic errors are caught by `pytest -m "not gpu"` before a GPU call is spent.
+// It is not linked into libtw_b200.so and the package never loads it: the product has no CPU
+// path.  Orchestration mirrors tw_score.cu (k_score) and tw_stitch.cu (k_stitch).
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../traceweaver_b200/csrc/tw_core.cuh"
+
+using namespace tw;
+
+static ParamView param_view(const tw_params* prm, const ProbView& v, int p, int i) {
+  ParamView pv;
+  pv.mode = prm->mode;
+  pv.gauss = nullptr;
+  pv.mix = nullptr;
+  if (prm->mode == TW_PARAMS_GAUSS_BATCHED)
+    pv.gauss = prm->gauss + (prm->prob_gauss_off[p] + (int64_t)(i / TW_PARAM_BATCH) * v.n_terms) * TW_GAUSS_REC;
+  else
+    pv.mix = prm->mix + (int64_t)v.term0 * TW_MIX_REC;
+  return pv;
+}
+
+extern "C" int twe_score_problem(const tw_batch* b, int p, const tw_params* prm, const tw_score_out* out,
+                                 int W, int* overflow) {
+  ProbView v;
+  int rc = load_view(*b, p, v);
+  if (rc) return rc;
+  int n = v.n_in;
+  // exclusive prefix arg-max of in_end, ties to the later index (k_prev_index)
+  std::vector<int> prev(n, 0);
+  for (int i = 1; i < n; ++i) {
+    int pr = prev[i - 1];
+    if (i >= 2 && v.ie[i - 1] >= v.ie[pr]) pr = i - 1;
+    if (i == 1) pr = 0;
+    prev[i] = pr;
+  }
+  std::vector<uint32_t> used((size_t)n * TW_MAX_E * W, 0u);
+  std::vector<int> lo_abs((size_t)n * TW_MAX_E, 0);
+  OutWin w[TW_MAX_E];
+  for (int e = 0; e < v.E; ++e) w[e] = OutWin{v.os[e], v.oe[e], 0, v.n_out[e]};
+  *overflow = 0;
+  for (int i = 0; i < n; ++i) {
+    int lo[TW_MAX_E];
+    for (int e = 0; e < v.E; ++e) {
+      lo[e] = lower_bound(w[e].s, w[e].n, v.is[i]);
+      lo_abs[(size_t)i * TW_MAX_E + e] = lo[e];
+    }
+    TopK tk; tk.n = 0;
+    long long leaves = 0;
+    uint32_t* mine = &used[(size_t)i * TW_MAX_E * W];
+    ParamView pv;
+    if (prm) pv = param_view(prm, v, p, i);
+    int64_t in_s = v.is[i], in_e = v.ie[i];
+    enumerate(v, in_s, in_e, w, lo, [](int, int) { return false; },
+              [&](const int* c, const int64_t* cs, const int64_t* ce) {
+                ++leaves;
+                for (int e = 0; e < v.E; ++e) {
+                  int bit = c[e] - lo[e];
+                  if (bit >= 32 * W) { *overflow = 1; continue; }
+                  mine[e * W + (bit >> 5)] |= 1u << (bit & 31);
+                }
+                if (prm) topk_offer(v, tk, score_tuple(v, pv, in_s, in_e, cs, ce), c);
+              });
+    out->n_feasible[v.in_off + i] = (int32_t)leaves;
+    if (prm && out->topk_score) {
+      out->topk_cnt[v.in_off + i] = (uint8_t)tk.n;
+      for (int k = 0; k < TW_K; ++k) {
+        out->topk_score[(v.in_off + i) * TW_K + k] = k < tk.n ? tk.score[k] : NAN;
+        for (int e = 0; e < v.E; ++e)
+          out->topk_idx[TW_K * (v.tuple_off + (int64_t)i * v.E) + k * v.E + e] = k < tk.n ? tk.idx[k][e] : -1;
+      }
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    uint8_t cut = 0;
+    if (i >= 1 && i <= n - 2) {
+      int pi = prev[i];
+      bool disjoint = true;
+      for (int e = 0; e < v.E && disjoint; ++e)
+        if (bitmaps_intersect(&used[((size_t)pi * TW_MAX_E + e) * W], lo_abs[(size_t)pi * TW_MAX_E + e],
+                              &used[((size_t)i * TW_MAX_E + e) * W], lo_abs[(size_t)i * TW_MAX_E + e], W))
+          disjoint = false;
+      cut = (uint8_t)(disjoint && v.ie[pi] <= v.ie[i]);
+    }
+    out->cut[v.in_off + i] = cut;
+  }
+  return TW_OK;
+}
+
+extern "C" int twe_stitch_problem(const tw_batch* b, int p, const tw_params* prm, const uint8_t* cut_all,
+                                  const tw_pass_out* out, long long node_limit) {
+  ProbView v;
+  int rc = load_view(*b, p, v);
+  if (rc) return rc;
+  int n = v.n_in;
+  const uint8_t* cut = cut_all + v.in_off;
+  std::vector<std::vector<uint8_t>> taken(v.E);
+  for (int e = 0; e < v.E; ++e) taken[e].assign((size_t)v.n_out[e], 0);
+  OutWin w[TW_MAX_E];
+  for (int e = 0; e < v.E; ++e) w[e] = OutWin{v.os[e], v.oe[e], 0, v.n_out[e]};
+  for (int e = 0; e < v.E; ++e)
+    for (int i = 0; i < n; ++i) out->assign[v.tuple_off + (int64_t)e * n + i] = -1;
+  for (int i = 0; i < n; ++i) out->mis_rank[v.in_off + i] = -1;
+  WindowCursor wc; wc.init();
+  WindowBuf* wb = new WindowBuf;
+  int cursor[TW_MAX_E] = {0};
+  int not_best = 0, unassigned = 0; long long max_nodes = 0;
+  int ws = 0;
+  while (ws < n) {
+    int we = ws;
+    while (!wc.ends_at(we, n, cut) && we < n - 1) ++we;
+    bool closes = (we != n - 1) || (n > 1);
+    int nw = we - ws + 1;
+    if (nw > TW_WINDOW_CAP) { delete wb; return TW_ERR_INVALID; }
+    for (int l = 0; l < nw; ++l) {  // one lane per in-span of the window
+      int i = ws + l;
+      int lo[TW_MAX_E];
+      for (int e = 0; e < v.E; ++e) lo[e] = lower_bound_from(w[e].s, w[e].n, cursor[e], v.is[i]);
+      if (l == 0) for (int e = 0; e < v.E; ++e) cursor[e] = lo[e];
+      TopK tk; tk.n = 0;
+      long long leaves = 0;
+      ParamView pv = param_view(prm, v, p, i);
+      int64_t in_s = v.is[i], in_e = v.ie[i];
+      enumerate(v, in_s, in_e, w, lo, [&](int e, int o) { return taken[e][o] != 0; },
+                [&](const int* c, const int64_t* cs, const int64_t* ce) {
+                  ++leaves;
+                  topk_offer(v, tk, score_tuple(v, pv, in_s, in_e, cs, ce), c);
+                });
+      out->n_cand[v.in_off + i] = (int32_t)leaves;
+      wb->cnt[l] = tk.n;
+      for (int k = 0; k < tk.n; ++k) {
+        wb->score[l][k] = tk.score[k];
+        for (int e = 0; e < v.E; ++e) wb->idx[l][k][e] = tk.idx[k][e];
+      }
+      if (out->topk_score) {
+        out->topk_cnt[v.in_off + i] = (uint8_t)tk.n;
+        for (int k = 0; k < TW_K; ++k) {
+          out->topk_score[(v.in_off + i) * TW_K + k] = k < tk.n ? tk.score[k] : NAN;
+          for (int e = 0; e < v.E; ++e)
+            out->topk_idx[TW_K * (v.tuple_off + (int64_t)i * v.E) + k * v.E + e] = k < tk.n ? tk.idx[k][e] : -1;
+        }
+      }
+    }
+    if (closes) {
+      for (int l = 0; l < nw; ++l) wb->adj[l] = window_adjacency(*wb, v.E, nw, l);
+      long long nodes = mwis_solve(*wb, v.E, nw, node_limit);
+      if (nodes < 0) { delete wb; return TW_ERR_MWIS_LIMIT; }
+      if (nodes > max_nodes) max_nodes = nodes;
+      for (int l = 0; l < nw; ++l) {
+        int i = ws + l, r = wb->chosen[l];
+        out->mis_rank[v.in_off + i] = (int8_t)r;
+        if (r != 0) ++not_best;
+        if (r < 0) { ++unassigned; continue; }
+        for (int e = 0; e < v.E; ++e) {
+          int o = wb->idx[l][r][e];
+          out->assign[v.tuple_off + (int64_t)e * n + i] = o;
+          taken[e][o] = 1;
+        }
+      }
+    }
+    ws = we + 1;
+  }
+  if (out->counters) {
+    out->counters[p * 4 + 0] = not_best;
+    out->counters[p * 4 + 1] = unassigned;
+    out->counters[p * 4 + 2] = (int32_t)(max_nodes > 0x7fffffff ? 0x7fffffff : max_nodes);
+    out->counters[p * 4 + 3] = 0;
+  }
+  delete wb;
+  return TW_OK;
+}

@@ -1,0 +1,70 @@
+"""ctypes front end of tests/emul/libtw_emul.so: the engine's device functions (tw_core.cuh)
+compiled for the CPU and stepped sequentially.  Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from oracle.tw_oracle import OracleBatch, _ptr, _check
+from traceweaver_b200 import _abi
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul")
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        subprocess.check_call(["make", "-s", "-C", HERE, "libtw_emul.so"], stderr=subprocess.DEVNULL)
+        _LIB = C.CDLL(os.path.join(HERE, "libtw_emul.so"))
+    return _LIB
+
+
+class EmulBatch(OracleBatch):
+    """Same interface as OracleBatch, but running the engine's own per-thread code."""
+
+    W = 2              # bitmap words per (in-span, ep): the narrow kernel's width
+    node_limit = 0
+
+    def score(self, gauss=None, mix=None):
+        hb = self.hb
+        n = int(hb.prob_in_off[-1])
+        nt = int(hb.prob_tuple_off[-1])
+        res = dict(topk_score=np.full((n, _abi.TW_K), np.nan), topk_idx=np.full(_abi.TW_K * nt, -1, np.int32),
+                   topk_cnt=np.zeros(n, np.uint8), n_feasible=np.zeros(n, np.int32), cut=np.zeros(n, np.uint8))
+        out = _abi.TwScoreOut(*[_ptr(res[k]) for k in ("topk_score", "topk_idx", "topk_cnt", "n_feasible", "cut")])
+        have = gauss is not None or mix is not None
+        prm = self._params_struct(gauss, mix) if have else None
+        self.overflow = []
+        for p in range(hb.n_problems):
+            ov = C.c_int(0)
+            W = self.W
+            _check(lib().twe_score_problem(C.byref(self.struct), p, C.byref(prm) if have else None,
+                                           C.byref(out), W, C.byref(ov)), "emul.score")
+            if ov.value:  # the engine re-runs overflowing tiles with the wide kernel
+                W = 64
+                _check(lib().twe_score_problem(C.byref(self.struct), p, C.byref(prm) if have else None,
+                                               C.byref(out), W, C.byref(ov)), "emul.score")
+                assert not ov.value
+            self.overflow.append(W)
+        return res
+
+    def stitch(self, cut, gauss=None, mix=None, want_topk=True):
+        hb = self.hb
+        n = int(hb.prob_in_off[-1])
+        nt = int(hb.prob_tuple_off[-1])
+        res = dict(assign=np.full(nt, -1, np.int32), mis_rank=np.full(n, -1, np.int8),
+                   n_cand=np.zeros(n, np.int32),
+                   topk_score=np.full((n, _abi.TW_K), np.nan) if want_topk else None,
+                   topk_idx=np.full(_abi.TW_K * nt, -1, np.int32) if want_topk else None,
+                   topk_cnt=np.zeros(n, np.uint8) if want_topk else None,
+                   counters=np.zeros((hb.n_problems, 4), np.int32))
+        out = _abi.TwPassOut(*[_ptr(res[k]) for k in ("assign", "mis_rank", "n_cand", "topk_score", "topk_idx",
+                                                      "topk_cnt", "counters")])
+        prm = self._params_struct(gauss, mix)
+        cut = np.ascontiguousarray(cut, np.uint8)
+        for p in range(hb.n_problems):
+            _check(lib().twe_stitch_problem(C.byref(self.struct), p, C.byref(prm), _ptr(cut), C.byref(out),
+                                            C.c_longlong(self.node_limit)), "emul.stitch")
+        return res

@@ -1,0 +1,460 @@
+// tw_core.cuh — per-thread building blocks of the span-assignment engine.
+//
+// Everything here is `__host__ __device__` on purpose: the CUDA kernels (tw_score.cu,
+// tw_stitch.cu, ...) are thin cooperative wrappers around these functions, and the build
+// container has no GPU, so tests/emul/ compiles the SAME functions with g++ and steps the kernels'
+// thread loops sequentially to unit-test the device logic on CPU.  That harness is test
+// infrastructure; the shipped library contains only the CUDA path.
+//
+// Reference semantics (file:line are in /root/reference/src/trace_reconstructor/ports/python/
+// algorithms/): V3 = traceweaver_v3.py, V1 = traceweaver_v1.py.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/traceweaver_b200.h"
+
+#if defined(__CUDACC__)
+#define TW_HD __host__ __device__ __forceinline__
+#define TW_HD_NOINLINE __host__ __device__
+#else
+#define TW_HD inline
+#define TW_HD_NOINLINE
+#endif
+
+#define TW_MAX_TERMS 48  // <= E(E-1)/2 primary edges + E roots + E lasts for E = 8
+#define TW_LOG_SQRT_2PI 0.91893853320467274178032973640562
+#define TW_LOG_2PI 1.8378770664093453
+
+namespace tw {
+
+// IEEE-exact f64 ops that the compiler may not contract into FMAs: scores must follow
+// scipy/sklearn operation order (contract: |delta| <= 1e-5, in practice ~1e-13).
+#if defined(__CUDA_ARCH__)
+TW_HD double dmul(double a, double b) { return __dmul_rn(a, b); }
+TW_HD double dadd(double a, double b) { return __dadd_rn(a, b); }
+TW_HD double dsub(double a, double b) { return __dsub_rn(a, b); }
+TW_HD double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+#else
+TW_HD double dmul(double a, double b) { volatile double r = a * b; return r; }
+TW_HD double dadd(double a, double b) { volatile double r = a + b; return r; }
+TW_HD double dsub(double a, double b) { volatile double r = a - b; return r; }
+TW_HD double ddiv(double a, double b) { volatile double r = a / b; return r; }
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// Likelihood terms: GetEpPairCost, V1:117-139.
+// ---------------------------------------------------------------------------------------------
+
+// scipy.stats.norm.logpdf(dt, mu, sigma) = -x^2/2 - log(sqrt(2 pi)) - log(sigma); rec = {mu,
+// sigma (already clamped, V1:130-131), log(sigma)}.
+TW_HD double gauss_logpdf(const double* rec, double dt) {
+  double x = ddiv(dsub(dt, rec[0]), rec[1]);
+  return dsub(dsub(-dmul(x, x) / 2.0, TW_LOG_SQRT_2PI), rec[2]);
+}
+
+// sklearn GaussianMixture.score of one sample (V1:125-126): logsumexp_k(log N_k + log w_k).
+// rec = {k, pc[5], mu*pc[5], log pc[5], log w[5]}; k == 0: Gaussian record at rec+1.
+TW_HD double mix_logpdf(const double* rec, double dt) {
+  int k = (int)rec[0];
+  if (k == 0) return gauss_logpdf(rec + 1, dt);
+  double a[TW_GMM_MAX_COMP];
+  double amax = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < TW_GMM_MAX_COMP; ++c) {
+    if (c < k) {
+      double y = dsub(dmul(dt, rec[1 + c]), rec[6 + c]);
+      a[c] = dadd(dadd(dmul(-0.5, dadd(TW_LOG_2PI, dmul(y, y))), rec[11 + c]), rec[16 + c]);
+      if (a[c] > amax) amax = a[c];
+    }
+  }
+  double s = 0.0, m = 0.0;
+#pragma unroll
+  for (int c = 0; c < TW_GMM_MAX_COMP; ++c) {
+    if (c < k) {
+      if (a[c] == amax) m += 1.0;
+      else s = dadd(s, exp(dsub(a[c], amax)));
+    }
+  }
+  if (m > 1.0) return dadd(dadd(log1p(ddiv(s, m)), log(m)), amax);
+  return dadd(log1p(s), amax);   // log(1) == 0 exactly
+}
+
+// ---------------------------------------------------------------------------------------------
+// Problem view (one service).  Pointers are problem-local bases into the batch arrays.
+// ---------------------------------------------------------------------------------------------
+struct ProbView {
+  int E, n_in, n_terms;
+  int ep0, term0;
+  int64_t in_off, tuple_off;
+  const int64_t* is;
+  const int64_t* ie;
+  const int64_t* os[TW_MAX_E];
+  const int64_t* oe[TW_MAX_E];
+  int64_t out_off[TW_MAX_E];
+  int n_out[TW_MAX_E];
+  uint32_t pred[TW_MAX_E];
+  int term_lo[TW_MAX_E + 1];
+  int8_t term_src[TW_MAX_TERMS];
+};
+
+TW_HD_NOINLINE inline int load_view(const tw_batch& b, int p, ProbView& v) {
+  v.ep0 = b.prob_ep_off[p];
+  v.E = b.prob_ep_off[p + 1] - v.ep0;
+  if (v.E < 1 || v.E > TW_MAX_E) return TW_ERR_INVALID;
+  v.in_off = b.prob_in_off[p];
+  v.n_in = (int)(b.prob_in_off[p + 1] - v.in_off);
+  v.tuple_off = b.prob_tuple_off[p];
+  v.is = b.in_start + v.in_off;
+  v.ie = b.in_end + v.in_off;
+  v.term0 = b.ep_term_off[v.ep0];
+  v.n_terms = b.ep_term_off[v.ep0 + v.E] - v.term0;
+  if (v.n_terms > TW_MAX_TERMS) return TW_ERR_INVALID;
+  for (int e = 0; e < v.E; ++e) {
+    int64_t o = b.ep_out_off[v.ep0 + e];
+    v.out_off[e] = o;
+    v.os[e] = b.out_start + o;
+    v.oe[e] = b.out_end + o;
+    v.n_out[e] = (int)(b.ep_out_off[v.ep0 + e + 1] - o);
+    v.pred[e] = b.ep_pred_mask[v.ep0 + e];
+    v.term_lo[e] = b.ep_term_off[v.ep0 + e] - v.term0;
+  }
+  v.term_lo[v.E] = v.n_terms;
+  for (int t = 0; t < v.n_terms; ++t) v.term_src[t] = b.term_src[v.term0 + t];
+  return TW_OK;
+}
+
+// Parameters as seen by one in-span: `gauss` points at the [n_terms][3] table of its 100-span
+// batch (V3:1173-1178), `mix` at the problem's [n_terms][21] table.
+struct ParamView {
+  int mode;
+  const double* gauss;
+  const double* mix;
+};
+
+TW_HD double term_logpdf(const ParamView& pv, int t, double dt) {
+  if (pv.mode == TW_PARAMS_GAUSS_BATCHED) return gauss_logpdf(pv.gauss + t * TW_GAUSS_REC, dt);
+  return mix_logpdf(pv.mix + t * TW_MIX_REC, dt);
+}
+
+// A window of an ep's out list: element x of the window is original index base + x.  The score
+// kernel points these at shared-memory staged copies, the stitch kernel at the global arrays.
+struct OutWin {
+  const int64_t* s;
+  const int64_t* e;
+  int base;
+  int n;
+};
+
+// ScoreAssignmentAsPerInvocationGraph, V1:305-361 (no skips, normalized = False).
+// cs/ce = start/end of the chosen out span per ep.
+TW_HD double score_tuple(const ProbView& v, const ParamView& pv, int64_t in_s, int64_t in_e,
+                         const int64_t* cs, const int64_t* ce) {
+  int last = 0;  // max(..., key = end) keeps the first maximum (V1:314)
+  for (int e = 1; e < v.E; ++e)
+    if (ce[e] > ce[last]) last = e;
+  double cost = 0.0;
+  for (int e = 0; e < v.E; ++e) {
+    for (int t = v.term_lo[e]; t < v.term_lo[e + 1]; ++t) {
+      int src = v.term_src[t];
+      int64_t d;
+      if (src >= 0) d = cs[e] - ce[src];                  // V1:345
+      else if (src == TW_TERM_ROOT) d = cs[e] - in_s;     // V1:349-350
+      else {                                              // V1:354-355
+        if (e != last) continue;
+        d = in_e - ce[e];
+      }
+      cost = dadd(cost, term_logpdf(pv, t, (double)d));
+    }
+  }
+  return cost;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Top-K list: V3:305-307 keeps the K largest (score, stack); V3:461 sorts descending.  Order:
+// score, then the first tuple position whose span differs decides by start (spans.py:51).
+// ---------------------------------------------------------------------------------------------
+struct TopK {
+  double score[TW_K];
+  int idx[TW_K][TW_MAX_E];
+  int n;
+};
+
+// a < b in the reference's (score, stack) order
+TW_HD bool cand_less(const ProbView& v, double sa, const int* ca, double sb, const int* cb) {
+  if (sa < sb) return true;
+  if (!(sa == sb)) return false;
+  for (int e = 0; e < v.E; ++e)
+    if (ca[e] != cb[e]) return v.os[e][ca[e]] < v.os[e][cb[e]];
+  return false;
+}
+
+TW_HD void topk_offer(const ProbView& v, TopK& tk, double score, const int* c) {
+  int pos = tk.n;
+  while (pos > 0 && cand_less(v, tk.score[pos - 1], tk.idx[pos - 1], score, c)) --pos;
+  if (pos >= TW_K) return;
+  int last = tk.n < TW_K ? tk.n : TW_K - 1;
+  for (int k = last; k > pos; --k) {
+    tk.score[k] = tk.score[k - 1];
+    for (int e = 0; e < v.E; ++e) tk.idx[k][e] = tk.idx[k - 1][e];
+  }
+  tk.score[pos] = score;
+  for (int e = 0; e < v.E; ++e) tk.idx[pos][e] = c[e];
+  if (tk.n < TW_K) tk.n++;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Candidate enumeration: DfsTraverseX V3:292-351 / DfsTraverse3 V3:236-288 in the no-skip
+// regime.  Feasible tuples = one not-taken out span per ep with
+//     in.start <= s.start, s.end <= in.end                      (V3:328-333)
+//     c_b.end <= s.start for every DAG predecessor b of the ep   (V3:335-347)
+// FindCutoffs (V3:182-217) only narrows the scan and never removes a feasible tuple (a feasible
+// c_e has c_e.start <= c_e.end <= c_s.start for every successor s), so it is not reproduced; the
+// scan per ep is [lo_e, first span with start > in.end).  The oracle keeps the literal cutoffs,
+// and parity between the two is what tests assert.
+//
+// Leaf is called with the original indices c[e] and the chosen spans' start/end.
+// Taken is `bool(int ep, int orig_index)`.
+// ---------------------------------------------------------------------------------------------
+template <class Taken, class Leaf>
+TW_HD void enumerate(const ProbView& v, int64_t in_s, int64_t in_e, const OutWin* w, const int* lo,
+                     Taken taken, Leaf leaf) {
+  int x[TW_MAX_E];
+  int c[TW_MAX_E];
+  int64_t cs[TW_MAX_E], ce[TW_MAX_E];
+  int e = 0;
+  x[0] = lo[0];
+  while (e >= 0) {
+    bool descended = false;
+    while (x[e] < w[e].n) {
+      int xi = x[e]++;
+      int64_t s = w[e].s[xi];
+      if (s > in_e) { x[e] = w[e].n; break; }   // sorted by start: nothing further fits
+      int64_t en = w[e].e[xi];
+      if (en > in_e) continue;
+      uint32_t pm = v.pred[e];
+      bool ok = true;
+      for (int b = 0; b < e; ++b)
+        if ((pm >> b & 1u) && ce[b] > s) { ok = false; break; }
+      if (!ok) continue;
+      int orig = w[e].base + xi;
+      if (taken(e, orig)) continue;
+      c[e] = orig; cs[e] = s; ce[e] = en;
+      if (e == v.E - 1) { leaf(c, cs, ce); continue; }
+      ++e;
+      x[e] = lo[e];
+      descended = true;
+      break;
+    }
+    if (!descended) --e;
+  }
+}
+
+// first index in [0, n) of a sorted array with a[idx] >= key
+TW_HD int lower_bound(const int64_t* a, int n, int64_t key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+// first index with a[idx] > key
+TW_HD int upper_bound(const int64_t* a, int n, int64_t key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (key < a[mid]) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+// lower_bound knowing the answer is >= from (galloping; in-spans arrive sorted by start)
+TW_HD int lower_bound_from(const int64_t* a, int n, int from, int64_t key) {
+  if (from >= n || a[from] >= key) return from;
+  int step = 1, lo = from, hi = from + 1;
+  while (hi < n && a[hi] < key) { lo = hi; step <<= 1; hi = lo + step; }
+  if (hi > n) hi = n;
+  // invariant: a[lo] < key, (hi == n or a[hi] >= key)
+  ++lo;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PerfectCut (V3:1024-1039) support: "used" bitmaps.  Bit j of ep e <=> out span lo_e + j appears
+// in some feasible tuple of the in-span (candidates_array, V3:1043-1051).
+// ---------------------------------------------------------------------------------------------
+// any common set bit between A (origin loA) and B (origin loB >= loA), both W words
+TW_HD bool bitmaps_intersect(const uint32_t* A, int loA, const uint32_t* B, int loB, int W) {
+  int shift = loB - loA;           // >= 0: in-spans are sorted by start
+  if (shift < 0) {                 // defensive: swap roles
+    const uint32_t* t = A; A = B; B = t; shift = -shift;
+  }
+  int ws = shift >> 5, bs = shift & 31;
+  for (int wi = 0; wi < W; ++wi) {
+    int ai = wi + ws;
+    if (ai >= W) break;
+    uint32_t a = A[ai] >> bs;
+    if (bs && ai + 1 < W) a |= A[ai + 1] << (32 - bs);
+    if (a & B[wi]) return true;
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-window stitch: BuildMISInstance (V3:1252-1274) + exact MWIS (gurobi_optimods.mwis at
+// V3:1411).  Vertices are (in-span k, rank r) with weight 10000 + score; two vertices conflict
+// when they belong to the same in-span or share an out span at the same tuple position
+// (AssignmentIntersect, V3:1276-1281).  Because every in-span's candidates form a clique, an
+// independent set picks at most one rank per in-span: branch and bound over in-spans ("rank r or
+// none"), after splitting the window into connected components of the in-span conflict graph.
+// Vertices with weight <= 0 are never taken (score < -10000).
+// ---------------------------------------------------------------------------------------------
+struct WindowBuf {
+  double score[TW_WINDOW_CAP][TW_K];
+  int idx[TW_WINDOW_CAP][TW_K][TW_MAX_E];
+  int cnt[TW_WINDOW_CAP];
+  int chosen[TW_WINDOW_CAP];
+  uint32_t adj[TW_WINDOW_CAP];
+};
+
+TW_HD bool tuples_conflict(const int* a, const int* b, int E) {
+  for (int e = 0; e < E; ++e)
+    if (a[e] == b[e]) return true;
+  return false;
+}
+
+// in-span level adjacency: bit a of adj[k] <=> some candidate of k conflicts with some of a
+TW_HD uint32_t window_adjacency(const WindowBuf& wb, int E, int nw, int k) {
+  uint32_t m = 0;
+  for (int a = 0; a < nw; ++a) {
+    if (a == k) continue;
+    bool hit = false;
+    for (int r = 0; r < wb.cnt[k] && !hit; ++r)
+      for (int q = 0; q < wb.cnt[a] && !hit; ++q)
+        hit = tuples_conflict(wb.idx[k][r], wb.idx[a][q], E);
+    if (hit) m |= 1u << a;
+  }
+  return m;
+}
+
+// Solves the window; wb.adj must be filled.  Returns the number of search nodes, or -1 when
+// node_limit is exceeded (TW_ERR_MWIS_LIMIT).
+TW_HD_NOINLINE inline long long mwis_solve(WindowBuf& wb, int E, int nw, long long node_limit) {
+  long long nodes = 0;
+  uint32_t todo = nw >= 32 ? 0xffffffffu : ((1u << nw) - 1u);
+  for (int k = 0; k < nw; ++k) wb.chosen[k] = -1;
+  while (todo) {
+    // connected component of the lowest remaining in-span
+    int seed = 0;
+    while (!(todo >> seed & 1u)) ++seed;
+    uint32_t comp = 1u << seed, frontier = comp;
+    while (frontier) {
+      int k = 0;
+      while (!(frontier >> k & 1u)) ++k;
+      frontier &= ~(1u << k);
+      uint32_t nb = wb.adj[k] & ~comp;
+      comp |= nb;
+      frontier |= nb;
+    }
+    todo &= ~comp;
+    int member[TW_WINDOW_CAP];
+    int m = 0;
+    for (int k = 0; k < nw; ++k)
+      if (comp >> k & 1u) member[m++] = k;
+    if (m == 1) {  // isolated in-span: its best candidate, if the weight is positive
+      int k = member[0];
+      if (wb.cnt[k] > 0 && TW_WEIGHT_OFFSET + wb.score[k][0] > 0.0) wb.chosen[k] = 0;
+      ++nodes;
+      continue;
+    }
+    double ub[TW_WINDOW_CAP + 1];
+    ub[m] = 0.0;
+    for (int l = m - 1; l >= 0; --l) {
+      int k = member[l];
+      double mx = 0.0;
+      for (int r = 0; r < wb.cnt[k]; ++r) {
+        double w = TW_WEIGHT_OFFSET + wb.score[k][r];
+        if (w > mx) mx = w;
+      }
+      ub[l] = ub[l + 1] + mx;
+    }
+    int choice[TW_WINDOW_CAP], best[TW_WINDOW_CAP], iter[TW_WINDOW_CAP + 1];
+    double cur[TW_WINDOW_CAP + 1];
+    double best_w = -1.0;
+    for (int l = 0; l < m; ++l) best[l] = -1;
+    int level = 0;
+    cur[0] = 0.0;
+    iter[0] = 0;
+    while (level >= 0) {
+      if (level == m) {
+        ++nodes;
+        if (cur[m] > best_w) {
+          best_w = cur[m];
+          for (int l = 0; l < m; ++l) best[l] = choice[l];
+        }
+        --level;
+        continue;
+      }
+      int k = member[level];
+      if (iter[level] == 0) {
+        ++nodes;
+        if (node_limit > 0 && nodes > node_limit) return -1;
+        if (cur[level] + ub[level] <= best_w) { --level; continue; }
+      }
+      int r = iter[level]++;
+      if (r > wb.cnt[k]) { --level; continue; }
+      if (r == wb.cnt[k]) {  // leave in-span k unassigned
+        choice[level] = -1;
+        cur[level + 1] = cur[level];
+        ++level;
+        iter[level] = 0;
+        continue;
+      }
+      double w = TW_WEIGHT_OFFSET + wb.score[k][r];
+      if (!(w > 0.0)) continue;
+      bool ok = true;
+      for (int l = 0; l < level && ok; ++l)
+        if (choice[l] >= 0 && (wb.adj[k] >> member[l] & 1u) &&
+            tuples_conflict(wb.idx[k][r], wb.idx[member[l]][choice[l]], E))
+          ok = false;
+      if (!ok) continue;
+      choice[level] = r;
+      cur[level + 1] = cur[level] + w;
+      ++level;
+      iter[level] = 0;
+    }
+    for (int l = 0; l < m; ++l) wb.chosen[member[l]] = best[l];
+  }
+  return nodes;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Windows from cut flags: CreateWindows2's loop, V3:1056-1076, as a cursor the stitch kernel
+// advances once per in-span.  cut[i] = PerfectCut(i) for 1 <= i <= n-2 and 0 elsewhere.
+//   visit n-1                          -> window ends at n-1
+//   visit i, cut[i]                    -> window ended at i-1 (seen here as look-ahead), count = 0
+//   visit i, else current_count == 30  -> window ends at i, count = 0
+// A window that starts at a perfect cut can hold 31 in-spans (the count restarts at 0 there,
+// at 1 after a size cut): TW_WINDOW_CAP.
+// ---------------------------------------------------------------------------------------------
+struct WindowCursor {
+  int count;
+  TW_HD void init() { count = 1; }
+  TW_HD bool ends_at(int i, int n, const uint8_t* cut) {
+    if (i == n - 1) return i != 0;
+    bool end = false;
+    if (i != 0) {
+      if (cut[i]) count = 0;
+      else if (count == TW_MAX_WINDOW) { count = 0; end = true; }
+    }
+    count += 1;
+    if (cut[i + 1]) end = true;
+    return end;
+  }
+};
+
+}  // namespace tw
