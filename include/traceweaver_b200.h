@@ -122,54 +122,70 @@ typedef struct tw_score_out {
   uint8_t* cut;           /* [n_in_total] 1 iff PerfectCut(i) (v3:1024-1039); cut[first]=0         */
 } tw_score_out;
 
-typedef struct tw_engine tw_engine;   /* opaque: device scratch, CUDA graph cache, error string  */
+typedef struct tw_engine tw_engine;   /* opaque: bound batch, device scratch, error string       */
 
 /* Library / device probing. */
 int tw_abi_version(void);
 const char* tw_last_error(void);
 int tw_device_count(void);
 
-/* Engine lifetime.  `device` is a CUDA ordinal; scratch grows on demand and is reused. */
+/* Engine lifetime.  `device` is a CUDA ordinal. */
 int tw_engine_create(int device, tw_engine** out);
 int tw_engine_destroy(tw_engine* eng);
 
-/* Host-side validation of descriptor arrays given as HOST pointers (same struct, host copies of
- * the small arrays; span arrays may be NULL).  Mirrors the asserts at v3:1088,1198. */
+/* Host-side validation of descriptor arrays given as HOST pointers (span arrays ignored).
+ * Mirrors the asserts at v3:1088,1198 and the engine limits. */
 int tw_batch_validate_host(const tw_batch* host_desc);
+
+/*
+ * Bind a batch.  `dev` holds DEVICE pointers (all fields); `host_desc` holds HOST copies of the
+ * descriptor arrays (prob_*, ep_*, term_src; its span pointers are ignored).  Validates the
+ * descriptors (the asserts of v3:1088,1198 plus engine limits), rejects skip budgets
+ * (n_out != n_in -> TW_ERR_UNSUPPORTED), builds the tile lists and allocates scratch, and runs the
+ * batch-constant pre-kernels (prev-index scan for PerfectCut v3:1026-1032, sorted end times for
+ * v3:624-645).  The arrays behind `dev` must stay alive and unchanged while bound.
+ */
+int tw_engine_bind(tw_engine* eng, const tw_batch* dev, const tw_batch* host_desc, void* stream);
+
+/* Blocks until `stream` is idle and returns the sticky device-side status of the kernels
+ * launched since the last call (TW_OK, TW_ERR_MWIS_LIMIT, TW_ERR_RANGE_LIMIT, ...). */
+int tw_engine_status(tw_engine* eng, void* stream);
+
+/* Number of kernels this engine has launched since creation (bench.py's gpu_launches). */
+int64_t tw_engine_launch_count(const tw_engine* eng);
 
 /*
  * Pass-0 parameters on the device: order-statistics mean/std per term per 100-in-span batch.
  * Replaces ComputeEpPairDistParams3 (traceweaver_v3.py:580-646) incl. scipy.stats.tstd.
- * Writes prob_gauss_off[P]-addressed records into `gauss_out`.
+ * gauss_out: [prob_gauss_off[P]] records of TW_GAUSS_REC doubles; prob_gauss_off (device, [P+1])
+ * = cumulative n_batches_p * n_terms_p.
  */
-int tw_params_pass0(tw_engine* eng, const tw_batch* b, const int64_t* prob_gauss_off,
-                    double* gauss_out, void* stream);
+int tw_params_pass0(tw_engine* eng, const int64_t* prob_gauss_off, double* gauss_out, void* stream);
 
 /*
  * Candidate enumeration + scoring + top-K on the UNDELETED lists, plus perfect-cut flags.
  * Replaces FindTopKAssignments(K=5, out_span_partitions) (v3:1185, :180-465 with DfsTraverseX
  * :292-351 and ScoreAssignmentAsPerInvocationGraph v1:259-361 / GetEpPairCost v1:117-139) and
  * the pre-processing half of CreateWindows2 (v3:1041-1051 + PerfectCut :1024-1039).
- * `params` may be NULL: windows only (no scoring).
+ * `params` may be NULL: windows only (no scoring, topk_* untouched).
  */
-int tw_score_topk(tw_engine* eng, const tw_batch* b, const tw_params* params,
-                  const tw_score_out* out, void* stream);
+int tw_score_topk(tw_engine* eng, const tw_params* params, const tw_score_out* out, void* stream);
 
 /*
  * The sequential part of one pass: windows from cut flags (v3:1056-1076), per in-span top-K on
  * the not-yet-taken out spans (v3:1182), exact MWIS per window (BuildMISInstance v3:1252-1274 +
  * gurobi_optimods.mwis at v3:1411), assignment + deletion (AddAssignment v1:433-463).
  */
-int tw_stitch(tw_engine* eng, const tw_batch* b, const tw_params* params,
-              const uint8_t* cut, const tw_pass_out* out, void* stream);
+int tw_stitch(tw_engine* eng, const tw_params* params, const uint8_t* cut, const tw_pass_out* out,
+              void* stream);
 
 /*
  * Delay samples implied by a pass's assignments, per term (ComputeEpPairDistParams5's
  * `durations`, traceweaver_v3.py:721-760).  delays[term_sample_off[t] + j]; NA rows are dropped
  * and counts[t] receives the number of samples.  Sample capacity of term t of problem p = n_in_p.
  */
-int tw_delays(tw_engine* eng, const tw_batch* b, const int32_t* assign,
-              const int64_t* term_sample_off, double* delays, int32_t* counts, void* stream);
+int tw_delays(tw_engine* eng, const int32_t* assign, const int64_t* term_sample_off, double* delays,
+              int32_t* counts, void* stream);
 
 /*
  * Pass-boundary refit on the device: per term, 1-D Gaussian mixtures with 1..min(5,#unique)
@@ -182,18 +198,6 @@ int tw_delays(tw_engine* eng, const tw_batch* b, const int32_t* assign,
 int tw_gmm_refit(tw_engine* eng, int32_t n_terms, const int64_t* term_sample_off,
                  const double* delays, const int32_t* counts, uint32_t seed_select,
                  double* mix_out, int32_t* n_selected_out, void* stream);
-
-/*
- * Whole path, both passes, for a batch whose span arrays are already on the device:
- * params0 -> score (windows) -> stitch -> delays -> refit -> score (final top-K) -> stitch.
- * = TraceWeaverV3.FindAssignments v3:1087-1229 for every problem of the batch.
- * `final` receives the last pass; `topk_final` the no-deletion top-K of the last pass
- * (all_topk_assignments); n_cand_total[i] sums both passes (per_span_candidates is not reset
- * between iterations, v3:1093 vs :1159).
- */
-int tw_find_assignments(tw_engine* eng, const tw_batch* b, uint32_t seed_select,
-                        const tw_pass_out* final, const tw_score_out* topk_final,
-                        int32_t* n_cand_total, double* mix_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,136 @@
+"""GPU parity: the CUDA engine, called through the C ABI, against the golden vectors minted from
+the reference and against the CPU oracle on the same inputs.  Bit-exact for indices (top-K
+tuples, MWIS choice, assignments, cut flags, counts); |delta| <= 1e-5 for log-likelihood scores
+(north-star tolerance; observed ~1e-12)."""
+import numpy as np
+import pytest
+
+from golden_util import Golden, golden_files
+
+pytestmark = pytest.mark.gpu
+
+FILES = golden_files()
+IDS = [f.split("/")[-1][:-4] for f in FILES]
+SCORE_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("gpu-marked test needs a CUDA device")
+    return torch
+
+
+@pytest.fixture(scope="module")
+def engine(torch_cuda):
+    from traceweaver_b200.engine import Engine
+    eng = Engine(0)
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="module", params=FILES, ids=IDS)
+def case(request, engine):
+    from traceweaver_b200.batch import build_batch
+    g = Golden(request.param)
+    prob = g.problem()
+    hb = build_batch([prob])
+    engine.bind(hb)
+    return g, prob, hb, engine
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+def test_params_pass0(case):
+    from oracle import tw_oracle
+    g, prob, hb, eng = case
+    got = _np(eng.params_pass0().table)
+    eng.status()
+    want = g.gauss_table(prob).reshape(got.shape)
+    assert np.array_equal(got[:, 0], want[:, 0])                       # mean: exact integer ratio
+    np.testing.assert_allclose(got[:, 1], want[:, 1], rtol=1e-12)
+    np.testing.assert_allclose(got[:, 2], want[:, 2], rtol=0, atol=1e-12)
+    orc = tw_oracle.OracleBatch(hb).params_pass0()
+    assert np.array_equal(got[:, :2], orc[:, :2])                      # bit-exact vs the oracle
+
+
+def test_windows(case):
+    from oracle import tw_oracle
+    g, prob, hb, eng = case
+    res = eng.score()
+    eng.status()
+    assert tw_oracle.windows_from_cuts(_np(res["cut"])) == g.windows()
+    assert np.array_equal(_np(res["n_feasible"]), g.z["pre_cnt"])
+
+
+@pytest.mark.parametrize("pass_id", [0, 1])
+def test_topk_without_deletion(case, pass_id):
+    g, prob, hb, eng = case
+    prm = eng.params_from_host(gauss=g.gauss_table(prob)) if pass_id == 0 else eng.params_from_host(mix=g.mix_table(prob))
+    res = eng.score(prm)
+    eng.status()
+    n, E = prob.n_in, prob.E
+    assert np.array_equal(_np(res["topk_cnt"]), g.z["topk2_cnt"][pass_id])
+    np.testing.assert_allclose(_np(res["topk_score"]), g.z["topk2_score"][pass_id], rtol=0, atol=SCORE_TOL,
+                               equal_nan=True)
+    assert np.array_equal(_np(res["topk_idx"]).reshape(n, 5, E), g.z["topk2_idx"][pass_id])
+
+
+@pytest.mark.parametrize("pass_id", [0, 1])
+def test_hot_loop_pass(case, pass_id):
+    g, prob, hb, eng = case
+    cut = eng.score()["cut"]
+    prm = eng.params_from_host(gauss=g.gauss_table(prob)) if pass_id == 0 else eng.params_from_host(mix=g.mix_table(prob))
+    res = eng.stitch(prm, cut, want_topk=True)
+    eng.status()
+    n, E = prob.n_in, prob.E
+    assert np.array_equal(_np(res["topk_cnt"]), g.z["topk_cnt"][pass_id])
+    np.testing.assert_allclose(_np(res["topk_score"]), g.z["topk_score"][pass_id], rtol=0, atol=SCORE_TOL,
+                               equal_nan=True)
+    assert np.array_equal(_np(res["topk_idx"]).reshape(n, 5, E), g.z["topk_idx"][pass_id])
+    assert np.array_equal(_np(res["mis_rank"]), g.z["mis_rank"][pass_id])
+    if pass_id == 1:
+        assert np.array_equal(_np(res["assign"]).reshape(E, n), g.z["assign"])
+        c = _np(res["counters"])
+        assert c[0, 0] == g.meta["not_best_count"] and c[0, 1] == g.meta["cnt_unassigned"] and c[0, 3] == 0
+
+
+def test_delays_match_oracle(case):
+    from oracle import tw_oracle
+    g, prob, hb, eng = case
+    cut = eng.score()["cut"]
+    res = eng.stitch(eng.params_from_host(gauss=g.gauss_table(prob)), cut)
+    delays, counts = eng.delays(res["assign"])
+    eng.status()
+    ob = tw_oracle.OracleBatch(hb)
+    od, oc = ob.delays(_np(res["assign"]))
+    assert np.array_equal(_np(counts), oc)
+    assert np.array_equal(_np(delays)[: len(od)], od) or np.array_equal(
+        np.concatenate([_np(delays)[o:o + c] for o, c in zip(hb.term_sample_off[:-1], oc)]),
+        np.concatenate([od[o:o + c] for o, c in zip(hb.term_sample_off[:-1], oc)]))
+
+
+def test_all_goldens_in_one_batch(engine):
+    """Many services in one launch sequence: results must equal the per-service runs."""
+    from traceweaver_b200.batch import build_batch
+    gs = [Golden(f) for f in FILES]
+    probs = [g.problem() for g in gs]
+    hb = build_batch(probs)
+    engine.bind(hb)
+    gauss = np.concatenate([g.gauss_table(p).reshape(-1, 3) for g, p in zip(gs, probs)])
+    mix = np.concatenate([g.mix_table(p) for g, p in zip(gs, probs)])
+    cut = engine.score()["cut"]
+    r0 = engine.stitch(engine.params_from_host(gauss=gauss), cut)
+    r1 = engine.stitch(engine.params_from_host(mix=mix), cut)
+    engine.status()
+    a = _np(r1["assign"])
+    m0, m1 = _np(r0["mis_rank"]), _np(r1["mis_rank"])
+    for k, (g, p) in enumerate(zip(gs, probs)):
+        io, to = int(hb.prob_in_off[k]), int(hb.prob_tuple_off[k])
+        n, E = p.n_in, p.E
+        assert np.array_equal(m0[io:io + n], g.z["mis_rank"][0]), g.name
+        assert np.array_equal(m1[io:io + n], g.z["mis_rank"][1]), g.name
+        assert np.array_equal(a[to:to + n * E].reshape(E, n), g.z["assign"]), g.name

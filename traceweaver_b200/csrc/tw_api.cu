@@ -1,0 +1,299 @@
+// tw_api.cu — the C ABI of libtw_b200.so (include/traceweaver_b200.h): engine object, batch
+// binding (validation, tile lists, scratch), and the entry points that launch the kernels.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tw_kernels.cuh"
+
+using namespace tw;
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, const char* a = "", const char* b2 = "") {
+  char buf[512];
+  snprintf(buf, sizeof buf, fmt, a, b2);
+  g_last_error = buf;
+  return code;
+}
+
+#define CU(expr)                                                                      \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) return fail(TW_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+struct tw_engine {
+  int device = 0;
+  bool bound = false;
+  tw_batch dev{};
+  int64_t launches = 0;
+  // host descriptors
+  std::vector<int64_t> prob_in_off;
+  std::vector<int32_t> prob_ep_off;
+  int max_seg = 0;
+  // device scratch (owned)
+  std::vector<void*> owned;
+  int32_t* prev_idx = nullptr;
+  int32_t* narrow_tiles = nullptr;   // [2*n]: prob, start
+  int32_t* wide_tiles = nullptr;     // [3*n]: prob, start, narrow index
+  int n_narrow = 0, n_wide = 0;
+  uint8_t* narrow_overflow = nullptr;
+  uint32_t* taken = nullptr;
+  size_t taken_words = 0;
+  int* err_flag = nullptr;
+  int64_t* in_end_sorted = nullptr;
+  int64_t* out_end_sorted = nullptr;
+  int32_t* batch_prob = nullptr;
+  int32_t* batch_idx = nullptr;
+  int n_batches_total = 0;
+  int32_t* term_ep = nullptr;
+  int32_t* ep_prob = nullptr;
+  long long node_limit = 200000000LL;
+
+  void release() {
+    for (void* p : owned) cudaFree(p);
+    owned.clear();
+    bound = false;
+  }
+  template <class T>
+  cudaError_t alloc(T** out, size_t count) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(T));
+    if (e == cudaSuccess) { owned.push_back(p); *out = (T*)p; }
+    return e;
+  }
+};
+
+extern "C" {
+
+int tw_abi_version(void) { return TW_ABI_VERSION; }
+
+const char* tw_last_error(void) { return g_last_error.c_str(); }
+
+int tw_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int tw_engine_create(int device, tw_engine** out) {
+  if (!out) return fail(TW_ERR_INVALID, "tw_engine_create: out is NULL");
+  int n = tw_device_count();
+  if (device < 0 || device >= n) return fail(TW_ERR_NO_DEVICE, "tw_engine_create: no CUDA device %s", "");
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(TW_ERR_NO_DEVICE, "tw_engine_create: built for sm_100a, found %s", prop.name);
+  CU(cudaSetDevice(device));
+  tw_engine* e = new tw_engine;
+  e->device = device;
+  *out = e;
+  return TW_OK;
+}
+
+int tw_engine_destroy(tw_engine* eng) {
+  if (!eng) return TW_OK;
+  cudaSetDevice(eng->device);
+  eng->release();
+  delete eng;
+  return TW_OK;
+}
+
+int tw_batch_validate_host(const tw_batch* h) {
+  if (!h || h->n_problems < 1) return fail(TW_ERR_INVALID, "batch: no problems");
+  if (!h->prob_in_off || !h->prob_ep_off || !h->prob_tuple_off || !h->ep_out_off || !h->ep_term_off ||
+      !h->ep_pred_mask || !h->term_src)
+    return fail(TW_ERR_INVALID, "batch: NULL descriptor array");
+  const int P = h->n_problems;
+  if (h->prob_in_off[0] != 0 || h->prob_ep_off[0] != 0 || h->prob_tuple_off[0] != 0 || h->ep_out_off[0] != 0 ||
+      h->ep_term_off[0] != 0)
+    return fail(TW_ERR_INVALID, "batch: offsets must start at 0");
+  for (int p = 0; p < P; ++p) {
+    int E = h->prob_ep_off[p + 1] - h->prob_ep_off[p];
+    int64_t n = h->prob_in_off[p + 1] - h->prob_in_off[p];
+    if (E < 1 || E > TW_MAX_E) return fail(TW_ERR_INVALID, "batch: E outside [1, TW_MAX_E]");
+    if (n < 2 || n > 0x7fffffff) return fail(TW_ERR_INVALID, "batch: a problem needs >= 2 incoming spans");
+    if (h->prob_tuple_off[p + 1] - h->prob_tuple_off[p] != n * E)
+      return fail(TW_ERR_INVALID, "batch: prob_tuple_off inconsistent");
+    int ep0 = h->prob_ep_off[p];
+    int nt = h->ep_term_off[ep0 + E] - h->ep_term_off[ep0];
+    if (nt < E || nt > TW_MAX_TERMS) return fail(TW_ERR_INVALID, "batch: term count out of range");
+    for (int e = 0; e < E; ++e) {
+      int64_t no = h->ep_out_off[ep0 + e + 1] - h->ep_out_off[ep0 + e];
+      if (no != n) return fail(TW_ERR_UNSUPPORTED, "batch: n_out != n_in (skip budgets, SURVEY §8 f-4) unsupported");
+      uint32_t pm = h->ep_pred_mask[ep0 + e];
+      if (pm >> e) return fail(TW_ERR_INVALID, "batch: predecessor mask must reference earlier eps only");
+      int t0 = h->ep_term_off[ep0 + e], t1 = h->ep_term_off[ep0 + e + 1];
+      if (t1 <= t0 || h->term_src[t1 - 1] != TW_TERM_LAST) return fail(TW_ERR_INVALID, "batch: ep terms must end with LAST");
+      for (int t = t0; t < t1 - 1; ++t) {
+        int src = h->term_src[t];
+        if (src == TW_TERM_ROOT) { if (pm) return fail(TW_ERR_INVALID, "batch: ROOT term on an ep with in-edges"); }
+        else if (src < 0 || src >= e || !(pm >> src & 1u)) return fail(TW_ERR_INVALID, "batch: edge term without DAG edge");
+      }
+    }
+  }
+  if (h->prob_in_off[P] != h->n_in_total || h->ep_out_off[h->prob_ep_off[P]] != h->n_out_total ||
+      h->prob_ep_off[P] != h->n_ep_total || h->ep_term_off[h->n_ep_total] != h->n_term_total)
+    return fail(TW_ERR_INVALID, "batch: totals inconsistent");
+  return TW_OK;
+}
+
+int tw_engine_bind(tw_engine* eng, const tw_batch* dev, const tw_batch* h, void* stream_) {
+  if (!eng || !dev || !h) return fail(TW_ERR_INVALID, "tw_engine_bind: NULL argument");
+  cudaStream_t s = (cudaStream_t)stream_;
+  int rc = tw_batch_validate_host(h);
+  if (rc) return rc;
+  CU(cudaSetDevice(eng->device));
+  eng->release();
+  eng->dev = *dev;
+  const int P = h->n_problems;
+  eng->prob_in_off.assign(h->prob_in_off, h->prob_in_off + P + 1);
+  eng->prob_ep_off.assign(h->prob_ep_off, h->prob_ep_off + P + 1);
+
+  // ---- tile lists (a tile never crosses a problem; wide tiles subdivide narrow ones)
+  std::vector<int32_t> nt_prob, nt_start, wt_prob, wt_start, wt_narrow, bprob, bidx;
+  const int wide_len = kWideThreads - 1;
+  eng->max_seg = 0;
+  for (int p = 0; p < P; ++p) {
+    int n = (int)(h->prob_in_off[p + 1] - h->prob_in_off[p]);
+    if (n > eng->max_seg) eng->max_seg = n;
+    for (int i0 = 0; i0 < n; i0 += kScoreTile) {
+      int narrow_id = (int)nt_prob.size();
+      nt_prob.push_back(p);
+      nt_start.push_back(i0);
+      int lim = i0 + kScoreTile < n ? i0 + kScoreTile : n;
+      for (int j0 = i0; j0 < lim; j0 += wide_len) {
+        // wide tiles must not run past their narrow tile: tile_len is clamped in-kernel by n only,
+        // so sub-tiles are cut at narrow boundaries by listing them explicitly with their length
+        wt_prob.push_back(p);
+        wt_start.push_back(j0);
+        wt_narrow.push_back(narrow_id);
+      }
+    }
+    int nb = (n + TW_PARAM_BATCH - 1) / TW_PARAM_BATCH;
+    for (int q = 0; q < nb; ++q) { bprob.push_back(p); bidx.push_back(q); }
+  }
+  eng->n_narrow = (int)nt_prob.size();
+  eng->n_wide = (int)wt_prob.size();
+  eng->n_batches_total = (int)bprob.size();
+  std::vector<int32_t> term_ep(h->n_term_total), ep_prob(h->n_ep_total);
+  for (int p = 0; p < P; ++p)
+    for (int ep = h->prob_ep_off[p]; ep < h->prob_ep_off[p + 1]; ++ep) {
+      ep_prob[ep] = p;
+      for (int t = h->ep_term_off[ep]; t < h->ep_term_off[ep + 1]; ++t) term_ep[t] = ep;
+    }
+
+  CU(eng->alloc(&eng->prev_idx, (size_t)h->n_in_total));
+  CU(eng->alloc(&eng->narrow_tiles, (size_t)eng->n_narrow * 2));
+  CU(eng->alloc(&eng->wide_tiles, (size_t)eng->n_wide * 3));
+  CU(eng->alloc(&eng->narrow_overflow, (size_t)eng->n_narrow));
+  eng->taken_words = (size_t)(h->n_out_total / 32) + (size_t)h->n_ep_total + 2;
+  CU(eng->alloc(&eng->taken, eng->taken_words));
+  CU(eng->alloc(&eng->err_flag, 1));
+  CU(eng->alloc(&eng->in_end_sorted, (size_t)h->n_in_total));
+  CU(eng->alloc(&eng->out_end_sorted, (size_t)h->n_out_total));
+  CU(eng->alloc(&eng->batch_prob, bprob.size()));
+  CU(eng->alloc(&eng->batch_idx, bidx.size()));
+  CU(eng->alloc(&eng->term_ep, term_ep.size()));
+  CU(eng->alloc(&eng->ep_prob, ep_prob.size()));
+  auto up = [&](void* dst, const std::vector<int32_t>& src) {
+    return cudaMemcpyAsync(dst, src.data(), src.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+  };
+  CU(up(eng->narrow_tiles, nt_prob));
+  CU(up(eng->narrow_tiles + eng->n_narrow, nt_start));
+  CU(up(eng->wide_tiles, wt_prob));
+  CU(up(eng->wide_tiles + eng->n_wide, wt_start));
+  CU(up(eng->wide_tiles + 2 * eng->n_wide, wt_narrow));
+  CU(up(eng->batch_prob, bprob));
+  CU(up(eng->batch_idx, bidx));
+  CU(up(eng->term_ep, term_ep));
+  CU(up(eng->ep_prob, ep_prob));
+  CU(cudaMemsetAsync(eng->err_flag, 0, sizeof(int), s));
+  CU(cudaStreamSynchronize(s));   // staging vectors go out of scope
+
+  // ---- batch-constant pre-kernels
+  CU(launch_prev_index(eng->dev, eng->prev_idx, s));
+  if (eng->max_seg > 16384) return fail(TW_ERR_RANGE_LIMIT, "bind: a service has more than 16384 spans per list (sort limit)");
+  CU(launch_sort_ends(eng->dev, eng->in_end_sorted, eng->out_end_sorted, eng->max_seg, eng->err_flag, s));
+  eng->launches += 2;
+  eng->bound = true;
+  return TW_OK;
+}
+
+int tw_engine_status(tw_engine* eng, void* stream_) {
+  if (!eng) return fail(TW_ERR_INVALID, "tw_engine_status: NULL engine");
+  cudaStream_t s = (cudaStream_t)stream_;
+  int flag = 0;
+  CU(cudaMemcpyAsync(&flag, eng->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (flag != 0) {
+    CU(cudaMemsetAsync(eng->err_flag, 0, sizeof(int), s));
+    return fail(flag, "device-side status %s", flag == TW_ERR_MWIS_LIMIT ? "TW_ERR_MWIS_LIMIT"
+                                               : flag == TW_ERR_RANGE_LIMIT ? "TW_ERR_RANGE_LIMIT" : "error");
+  }
+  return TW_OK;
+}
+
+int64_t tw_engine_launch_count(const tw_engine* eng) { return eng ? eng->launches : 0; }
+
+static int need_bound(tw_engine* eng, const char* who) {
+  if (!eng || !eng->bound) return fail(TW_ERR_INVALID, "%s: no batch bound", who);
+  cudaError_t e = cudaSetDevice(eng->device);
+  if (e != cudaSuccess) return fail(TW_ERR_CUDA, "%s: %s", who, cudaGetErrorString(e));
+  return TW_OK;
+}
+
+int tw_params_pass0(tw_engine* eng, const int64_t* prob_gauss_off, double* gauss_out, void* stream) {
+  int rc = need_bound(eng, "tw_params_pass0");
+  if (rc) return rc;
+  CU(launch_params0(eng->dev, eng->in_end_sorted, eng->out_end_sorted, prob_gauss_off, eng->batch_prob,
+                    eng->batch_idx, eng->n_batches_total, gauss_out, (cudaStream_t)stream));
+  eng->launches += 1;
+  return TW_OK;
+}
+
+int tw_score_topk(tw_engine* eng, const tw_params* params, const tw_score_out* out, void* stream) {
+  int rc = need_bound(eng, "tw_score_topk");
+  if (rc) return rc;
+  if (!out || !out->cut || !out->n_feasible) return fail(TW_ERR_INVALID, "tw_score_topk: cut and n_feasible are required");
+  if (params && (!out->topk_score || !out->topk_idx || !out->topk_cnt))
+    return fail(TW_ERR_INVALID, "tw_score_topk: params given but topk outputs missing");
+  TileList narrow{eng->narrow_tiles, eng->narrow_tiles + eng->n_narrow, eng->n_narrow, kScoreTile};
+  TileList wide{eng->wide_tiles, eng->wide_tiles + eng->n_wide, eng->n_wide, kWideThreads - 1};
+  CU(launch_score(eng->dev, params, *out, narrow, wide, eng->prev_idx, eng->narrow_overflow, eng->err_flag,
+                  (cudaStream_t)stream));
+  eng->launches += 2;
+  return TW_OK;
+}
+
+int tw_stitch(tw_engine* eng, const tw_params* params, const uint8_t* cut, const tw_pass_out* out, void* stream) {
+  int rc = need_bound(eng, "tw_stitch");
+  if (rc) return rc;
+  if (!params || !cut || !out || !out->assign || !out->mis_rank || !out->n_cand)
+    return fail(TW_ERR_INVALID, "tw_stitch: params, cut, assign, mis_rank, n_cand are required");
+  if (out->topk_score && (!out->topk_idx || !out->topk_cnt)) return fail(TW_ERR_INVALID, "tw_stitch: partial topk outputs");
+  CU(launch_stitch(eng->dev, *params, cut, *out, eng->taken, eng->taken_words, eng->node_limit, eng->err_flag,
+                   (cudaStream_t)stream));
+  eng->launches += 1;
+  return TW_OK;
+}
+
+int tw_delays(tw_engine* eng, const int32_t* assign, const int64_t* term_sample_off, double* delays,
+              int32_t* counts, void* stream) {
+  int rc = need_bound(eng, "tw_delays");
+  if (rc) return rc;
+  CU(launch_delays(eng->dev, assign, term_sample_off, eng->term_ep, eng->ep_prob, delays, counts,
+                   (cudaStream_t)stream));
+  eng->launches += 1;
+  return TW_OK;
+}
+
+int tw_gmm_refit(tw_engine*, int32_t, const int64_t*, const double*, const int32_t*, uint32_t, double*, int32_t*,
+                 void*) {
+  return fail(TW_ERR_UNSUPPORTED, "tw_gmm_refit: device refit not built yet (host refit via tw_delays)");
+}
+
+}  // extern "C"

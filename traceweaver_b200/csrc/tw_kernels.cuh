@@ -1,0 +1,49 @@
+// tw_kernels.cuh — launch-side declarations shared by the .cu files of libtw_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tw_core.cuh"
+
+namespace tw {
+
+// ---- score kernel geometry (tw_score.cu) ----------------------------------------------------
+constexpr int kScoreThreads = 128;               // one in-span per thread
+constexpr int kScoreTile = kScoreThreads - 1;    // in-spans per CTA; the last thread enumerates
+                                                 // the tile's carry-in "prev" in-span (PerfectCut)
+constexpr int kStageSpans = 2048;                // out spans staged in shared memory per tile
+constexpr int kNarrowW = 2;                      // bitmap words per (in-span, ep): 64 candidates
+constexpr int kWideW = 64;                       // overflow kernel: 2048 candidates per ep
+constexpr int kWideThreads = 32;                 // (31 in-spans + carry-in per CTA)
+
+// ---- stitch kernel geometry (tw_stitch.cu) --------------------------------------------------
+constexpr int kStitchWarps = 4;                  // one warp per problem
+
+struct EngineScratch;                            // tw_api.cu
+
+// Tiles: a tile never crosses a problem.  tile_prob[t], tile_start[t] (problem-local in-span).
+struct TileList {
+  const int32_t* tile_prob;
+  const int32_t* tile_start;
+  int n_tiles;
+  int tile_len;
+};
+
+cudaError_t launch_prev_index(const tw_batch& b, int32_t* prev_idx, cudaStream_t s);
+cudaError_t launch_score(const tw_batch& b, const tw_params* prm, const tw_score_out& out,
+                         const TileList& narrow, const TileList& wide, const int32_t* prev_idx,
+                         uint8_t* narrow_overflow, int* err_flag, cudaStream_t s);
+cudaError_t launch_stitch(const tw_batch& b, const tw_params& prm, const uint8_t* cut,
+                          const tw_pass_out& out, uint32_t* taken_words, size_t taken_n_words,
+                          long long node_limit, int* err_flag, cudaStream_t s);
+cudaError_t launch_sort_ends(const tw_batch& b, int64_t* in_end_sorted, int64_t* out_end_sorted,
+                             int max_seg, int* err_flag, cudaStream_t s);
+cudaError_t launch_params0(const tw_batch& b, const int64_t* in_end_sorted,
+                           const int64_t* out_end_sorted, const int64_t* prob_gauss_off,
+                           const int32_t* batch_prob, const int32_t* batch_idx, int n_batches_total,
+                           double* gauss_out, cudaStream_t s);
+cudaError_t launch_delays(const tw_batch& b, const int32_t* assign, const int64_t* term_sample_off,
+                          const int32_t* term_ep, const int32_t* ep_prob, double* delays,
+                          int32_t* counts, cudaStream_t s);
+
+}  // namespace tw

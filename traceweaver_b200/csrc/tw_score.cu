@@ -1,0 +1,285 @@
+// tw_score.cu — candidate enumeration + likelihood scoring + top-K on the undeleted lists, and
+// the perfect-cut flags, for every in-span of a batch.
+//
+// Replaces (reference: .../algorithms/traceweaver_v3.py = V3, traceweaver_v1.py = V1)
+//   FindTopKAssignments(K=5, out_span_partitions)   V3:1185  (DfsTraverseX V3:292-351,
+//       ScoreAssignmentAsPerInvocationGraph V1:259-361, GetEpPairCost V1:117-139)
+//   CreateWindows2 pre-processing + PerfectCut       V3:1020-1051
+//
+// Mapping to the machine: HBM-bound integer/f64 work, no tensor cores.  One CTA owns a TILE of
+// kScoreTile consecutive in-spans of one service (in-spans are sorted by start), one thread per
+// in-span.  Because both sides are sorted by start, all candidates of the tile lie in one
+// contiguous slice of each ep's out list: the slice's start/end timestamps are staged ONCE into
+// shared memory (coalesced 128-bit loads) and every search / DFS step then runs out of shared
+// memory; each out span is read from HBM about once per tile that overlaps it.  Likelihood
+// parameters of the tile's one or two 100-span batches are staged alongside.  Thread
+// kScoreThreads-1 enumerates the tile's carry-in "prev" in-span (the latest-ending in-span before
+// the tile) so that PerfectCut(i) = disjoint(cand(prev(i)), cand(i)) is resolved inside the CTA
+// from bitmaps in shared memory.  Tiles whose candidate ranges exceed the narrow bitmap width are
+// flagged and redone by a wide instantiation (fewer threads, 2048 candidates per ep).
+#include "tw_kernels.cuh"
+
+namespace tw {
+
+// ---------------------------------------------------------------------------------------------
+// prev_index(i) = arg max_{j < i} in_end[j], ties to the later j   (V3:1026-1032)
+// one warp per problem, shuffle scan
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_prev_index(tw_batch b, int32_t* __restrict__ prev_idx) {
+  int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  int lane = threadIdx.x & 31;
+  if (warp >= b.n_problems) return;
+  int64_t off = b.prob_in_off[warp];
+  int n = (int)(b.prob_in_off[warp + 1] - off);
+  const int64_t* ie = b.in_end + off;
+  int64_t cmax = INT64_MIN;
+  int cidx = 0;
+  for (int base = 0; base < n; base += 32) {
+    int i = base + lane;
+    int64_t v = i < n ? ie[i] : INT64_MIN;
+    int vi = i;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int64_t ov = __shfl_up_sync(0xffffffffu, v, d);
+      int oi = __shfl_up_sync(0xffffffffu, vi, d);
+      if (lane >= d && !(v >= ov)) { v = ov; vi = oi; }
+    }
+    if (!(v >= cmax)) { v = cmax; vi = cidx; }   // fold the carry (earlier elements)
+    int64_t pv = __shfl_up_sync(0xffffffffu, v, 1);
+    int pi = __shfl_up_sync(0xffffffffu, vi, 1);
+    if (lane == 0) { pv = cmax; pi = cidx; }
+    (void)pv;
+    if (i < n) prev_idx[off + i] = i == 0 ? 0 : pi;
+    cmax = __shfl_sync(0xffffffffu, v, 31);
+    cidx = __shfl_sync(0xffffffffu, vi, 31);
+  }
+}
+
+cudaError_t launch_prev_index(const tw_batch& b, int32_t* prev_idx, cudaStream_t s) {
+  int warps_per_block = 4;
+  int blocks = (b.n_problems + warps_per_block - 1) / warps_per_block;
+  k_prev_index<<<blocks, warps_per_block * 32, 0, s>>>(b, prev_idx);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// score kernel
+// ---------------------------------------------------------------------------------------------
+template <int T, int W>
+struct ScoreSmem {
+  ProbView v;
+  OutWin win[TW_MAX_E];
+  int64_t st_s[kStageSpans];
+  int64_t st_e[kStageSpans];
+  double prm[TW_MAX_TERMS * TW_MIX_REC];     // mixture table, or two Gaussian batch tables
+  uint32_t used[T][TW_MAX_E][W];
+  int lo_abs[T][TW_MAX_E];
+  int64_t red[T / 32];
+  int win_a[TW_MAX_E], win_n[TW_MAX_E];
+  int staged;
+  int overflow;
+  int rc;
+};
+
+template <int T, int W>
+__global__ void __launch_bounds__(T)
+k_score(tw_batch b, tw_params prm, int has_params, tw_score_out out, TileList tiles,
+        const int32_t* __restrict__ prev_idx, uint8_t* __restrict__ overflow_flag, int redo_only,
+        int* __restrict__ err_flag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ScoreSmem<T, W>& sm = *reinterpret_cast<ScoreSmem<T, W>*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int t = blockIdx.x;
+  int i0, cnt, p;
+  if (redo_only) {
+    // wide pass: narrow tile `blockIdx.y`-independent mapping — wide tiles subdivide narrow ones
+    // tiles.tile_prob/tile_start describe WIDE tiles; overflow_flag is indexed by the narrow tile
+    // each wide tile belongs to (stored in the upper entries of tile arrays by the host).
+    if (!overflow_flag[tiles.tile_start[tiles.n_tiles + t]]) return;
+  }
+  p = tiles.tile_prob[t];
+  i0 = tiles.tile_start[t];
+
+  if (tid == 0) {
+    sm.rc = load_view(b, p, sm.v);
+    sm.overflow = 0;
+  }
+  __syncthreads();
+  if (sm.rc != TW_OK) {
+    if (tid == 0) atomicMin(err_flag, sm.rc);
+    return;
+  }
+  const ProbView& v = sm.v;
+  const int n = v.n_in;
+  cnt = min(tiles.tile_len, n - i0);
+  const int E = v.E;
+  const bool helper = (tid == T - 1) && (i0 >= 1);
+  const bool worker = tid < cnt;
+  int i = i0 + tid;
+  if (helper) i = prev_idx[v.in_off + i0];
+  int64_t in_s = 0, in_e = INT64_MIN;
+  if (worker || helper) { in_s = v.is[i]; in_e = v.ie[i]; }
+
+  // ---- tile's candidate slice per ep: [lower_bound(start >= first in.start), upper_bound(start <= max in.end))
+  int64_t me = worker ? in_e : INT64_MIN;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    int64_t o = __shfl_xor_sync(0xffffffffu, me, d);
+    me = o > me ? o : me;
+  }
+  if ((tid & 31) == 0) sm.red[tid >> 5] = me;
+  __syncthreads();
+  if (tid < E) {
+    int64_t mx = sm.red[0];
+    for (int q = 1; q < T / 32; ++q) mx = sm.red[q] > mx ? sm.red[q] : mx;
+    int a = lower_bound(v.os[tid], v.n_out[tid], v.is[i0]);
+    int z = upper_bound(v.os[tid], v.n_out[tid], mx);
+    sm.win_a[tid] = a;
+    sm.win_n[tid] = z > a ? z - a : 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int tot = 0;
+    for (int e = 0; e < E; ++e) tot += sm.win_n[e];
+    sm.staged = tot <= kStageSpans;
+    int off = 0;
+    for (int e = 0; e < E; ++e) {
+      if (sm.staged) {
+        sm.win[e].s = sm.st_s + off; sm.win[e].e = sm.st_e + off;
+        sm.win[e].base = sm.win_a[e]; sm.win[e].n = sm.win_n[e];
+        off += sm.win_n[e];
+      } else {   // slice too large for shared memory: read the global arrays directly
+        sm.win[e].s = v.os[e]; sm.win[e].e = v.oe[e]; sm.win[e].base = 0; sm.win[e].n = v.n_out[e];
+      }
+    }
+  }
+  __syncthreads();
+  if (sm.staged) {
+    for (int e = 0; e < E; ++e) {
+      const int64_t* gs = v.os[e] + sm.win_a[e];
+      const int64_t* ge = v.oe[e] + sm.win_a[e];
+      int64_t* ds = const_cast<int64_t*>(sm.win[e].s);
+      int64_t* de = const_cast<int64_t*>(sm.win[e].e);
+      for (int x = tid; x < sm.win_n[e]; x += T) { ds[x] = gs[x]; de[x] = ge[x]; }
+    }
+  }
+  // ---- likelihood parameters of this tile
+  int batch0 = i0 / TW_PARAM_BATCH;
+  if (has_params) {
+    if (prm.mode == TW_PARAMS_GAUSS_BATCHED) {
+      int nrec = 2 * v.n_terms * TW_GAUSS_REC;
+      int nb = (n + TW_PARAM_BATCH - 1) / TW_PARAM_BATCH;
+      const double* src = prm.gauss + (prm.prob_gauss_off[p] + (int64_t)batch0 * v.n_terms) * TW_GAUSS_REC;
+      int avail = (nb - batch0) * v.n_terms * TW_GAUSS_REC;
+      if (nrec > avail) nrec = avail;
+      for (int x = tid; x < nrec; x += T) sm.prm[x] = src[x];
+    } else {
+      const double* src = prm.mix + (int64_t)v.term0 * TW_MIX_REC;
+      for (int x = tid; x < v.n_terms * TW_MIX_REC; x += T) sm.prm[x] = src[x];
+    }
+  }
+  for (int e = 0; e < TW_MAX_E; ++e)
+    for (int wq = 0; wq < W; ++wq) sm.used[tid][e][wq] = 0u;
+  __syncthreads();
+
+  // ---- per-thread enumeration
+  if (worker || helper) {
+    OutWin w[TW_MAX_E];
+    int lo[TW_MAX_E];
+    for (int e = 0; e < E; ++e) {
+      if (helper && sm.staged) {   // carry-in span lies before the staged slice: use global arrays
+        w[e].s = v.os[e]; w[e].e = v.oe[e]; w[e].base = 0; w[e].n = v.n_out[e];
+      } else {
+        w[e] = sm.win[e];
+      }
+      lo[e] = lower_bound(w[e].s, w[e].n, in_s);
+      sm.lo_abs[tid][e] = w[e].base + lo[e];
+    }
+    ParamView pv;
+    pv.mode = prm.mode;
+    pv.gauss = sm.prm + (i / TW_PARAM_BATCH - batch0) * v.n_terms * TW_GAUSS_REC;
+    pv.mix = sm.prm;
+    TopK tk;
+    tk.n = 0;
+    int leaves = 0;
+    bool ovf = false;
+    const bool do_score = has_params && worker;
+    uint32_t (*mine)[W] = sm.used[tid];
+    const int* lo_abs = sm.lo_abs[tid];
+    enumerate(v, in_s, in_e, w, lo, [](int, int) { return false; },
+              [&](const int* c, const int64_t* cs, const int64_t* ce) {
+                if (leaves < 0x7fffffff) ++leaves;
+                for (int e = 0; e < E; ++e) {
+                  int bit = c[e] - lo_abs[e];
+                  if (bit >= 32 * W) ovf = true;
+                  else mine[e][bit >> 5] |= 1u << (bit & 31);
+                }
+                if (do_score) topk_offer(v, tk, score_tuple(v, pv, in_s, in_e, cs, ce), c);
+              });
+    if (ovf) sm.overflow = 1;
+    if (worker) {
+      int64_t gi = v.in_off + i;
+      out.n_feasible[gi] = leaves;
+      if (do_score && out.topk_score) {
+        out.topk_cnt[gi] = (uint8_t)tk.n;
+        int32_t* ix = out.topk_idx + TW_K * (v.tuple_off + (int64_t)i * E);
+        for (int k = 0; k < TW_K; ++k) {
+          out.topk_score[gi * TW_K + k] = k < tk.n ? tk.score[k] : __longlong_as_double(0x7ff8000000000000LL);
+          for (int e = 0; e < E; ++e) ix[k * E + e] = k < tk.n ? tk.idx[k][e] : -1;
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- PerfectCut(i), V3:1034-1039
+  if (worker) {
+    uint8_t cut = 0;
+    if (i >= 1 && i <= n - 2) {
+      int pi = prev_idx[v.in_off + i];
+      int slot = pi >= i0 ? pi - i0 : T - 1;
+      bool disjoint = true;
+      for (int e = 0; e < E && disjoint; ++e)
+        if (bitmaps_intersect(sm.used[slot][e], sm.lo_abs[slot][e], sm.used[tid][e], sm.lo_abs[tid][e], W))
+          disjoint = false;
+      cut = (uint8_t)(disjoint && v.ie[pi] <= in_e);
+    }
+    out.cut[v.in_off + i] = cut;
+  }
+  if (tid == 0 && sm.overflow) {
+    if (redo_only) atomicMin(err_flag, (int)TW_ERR_RANGE_LIMIT);
+    else overflow_flag[t] = 1;
+  }
+}
+
+cudaError_t launch_score(const tw_batch& b, const tw_params* prm, const tw_score_out& out,
+                         const TileList& narrow, const TileList& wide, const int32_t* prev_idx,
+                         uint8_t* narrow_overflow, int* err_flag, cudaStream_t s) {
+  tw_params dummy;
+  dummy.mode = TW_PARAMS_MIXTURE; dummy.reserved0 = 0;
+  dummy.prob_gauss_off = nullptr; dummy.gauss = nullptr; dummy.mix = nullptr;
+  const tw_params& pr = prm ? *prm : dummy;
+  using SmN = ScoreSmem<kScoreThreads, kNarrowW>;
+  using SmW = ScoreSmem<kWideThreads, kWideW>;
+  auto kn = k_score<kScoreThreads, kNarrowW>;
+  auto kw = k_score<kWideThreads, kWideW>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e1 = cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmN));
+    cudaError_t e2 = cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmW));
+    if (e1 != cudaSuccess) return e1;
+    if (e2 != cudaSuccess) return e2;
+    attr_done = true;
+  }
+  cudaError_t e = cudaMemsetAsync(narrow_overflow, 0, (size_t)narrow.n_tiles, s);
+  if (e != cudaSuccess) return e;
+  kn<<<narrow.n_tiles, kScoreThreads, sizeof(SmN), s>>>(b, pr, prm != nullptr, out, narrow, prev_idx,
+                                                        narrow_overflow, 0, err_flag);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  kw<<<wide.n_tiles, kWideThreads, sizeof(SmW), s>>>(b, pr, prm != nullptr, out, wide, prev_idx,
+                                                     narrow_overflow, 1, err_flag);
+  return cudaGetLastError();
+}
+
+}  // namespace tw

@@ -1,0 +1,172 @@
+// tw_stitch.cu — the sequential half of one pass: windows, per in-span top-K on the not-yet-taken
+// out spans, exact MWIS per window, assignment + deletion.
+//
+// Replaces (V3 = traceweaver_v3.py, V1 = traceweaver_v1.py)
+//   window loop                      V3:1056-1076 (from the cut flags of tw_score.cu)
+//   FindTopKAssignments(out_copy)    V3:1182
+//   GetAssignmentsMIS / Gurobi_MIS   V3:1237-1274, 1395-1419
+//   AddAssignment(delete=True)       V1:433-463   -> "taken" bitmap instead of list.remove
+//
+// Window w's candidates exclude out spans consumed by windows < w, so a service is a sequential
+// chain of windows; services are independent.  One WARP owns one service and walks its windows in
+// order: lane l enumerates + scores in-span (window start + l) (a window holds <= 31 in-spans),
+// the candidates meet in shared memory, lanes build the in-span conflict masks in parallel, lane 0
+// runs the exact branch and bound, lanes write assignments and set taken bits.  Parallelism comes
+// from the number of services in the batch (25 000 in the 100 M-span configuration).
+#include "tw_kernels.cuh"
+
+namespace tw {
+
+struct StitchWarpSmem {
+  ProbView v;
+  WindowBuf wb;
+};
+
+__global__ void __launch_bounds__(kStitchWarps * 32)
+k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_pass_out out,
+         uint32_t* __restrict__ taken, long long node_limit, int* __restrict__ err_flag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp_in_block = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * kStitchWarps + warp_in_block;
+  if (p >= b.n_problems) return;
+  StitchWarpSmem& sm = reinterpret_cast<StitchWarpSmem*>(smem_raw)[warp_in_block];
+  int rc = TW_OK;
+  if (lane == 0) rc = load_view(b, p, sm.v);
+  rc = __shfl_sync(0xffffffffu, rc, 0);
+  __syncwarp();
+  if (rc != TW_OK) {
+    if (lane == 0) { atomicMin(err_flag, rc); if (out.counters) out.counters[p * 4 + 3] = rc; }
+    return;
+  }
+  const ProbView& v = sm.v;
+  WindowBuf& wb = sm.wb;
+  const int n = v.n_in, E = v.E;
+  const uint8_t* cut = cut_all + v.in_off;
+
+  // taken bitmap of (problem, ep): word-aligned region, see tw_api.cu (taken_words)
+  uint32_t* tk_base[TW_MAX_E];
+  OutWin w[TW_MAX_E];
+  for (int e = 0; e < E; ++e) {
+    tk_base[e] = taken + (v.out_off[e] >> 5) + (v.ep0 + e);
+    w[e].s = v.os[e]; w[e].e = v.oe[e]; w[e].base = 0; w[e].n = v.n_out[e];
+  }
+  // defaults
+  for (int i = lane; i < n; i += 32) out.mis_rank[v.in_off + i] = -1;
+  for (int64_t x = lane; x < (int64_t)n * E; x += 32) out.assign[v.tuple_off + x] = -1;
+
+  const double* gauss_base = prm.mode == TW_PARAMS_GAUSS_BATCHED
+                                 ? prm.gauss + prm.prob_gauss_off[p] * TW_GAUSS_REC : nullptr;
+  const double* mix_base = prm.mode == TW_PARAMS_MIXTURE ? prm.mix + (int64_t)v.term0 * TW_MIX_REC : nullptr;
+
+  WindowCursor wc;
+  wc.init();
+  int cursor[TW_MAX_E];
+  for (int e = 0; e < E; ++e) cursor[e] = 0;
+  int not_best = 0, unassigned = 0;
+  long long max_nodes = 0;
+  int ws = 0;
+  while (ws < n) {
+    // ---- window extent (uniform across the warp)
+    int we = ws;
+    while (!wc.ends_at(we, n, cut) && we < n - 1) ++we;
+    const int nw = we - ws + 1;
+    if (nw > TW_WINDOW_CAP) { rc = TW_ERR_INVALID; break; }
+
+    // ---- per-lane candidate search on the not-taken spans
+    int lo0[TW_MAX_E];
+    if (lane < nw) {
+      const int i = ws + lane;
+      const int64_t in_s = v.is[i], in_e = v.ie[i];
+      int lo[TW_MAX_E];
+      for (int e = 0; e < E; ++e) lo[e] = lower_bound_from(w[e].s, w[e].n, cursor[e], in_s);
+      for (int e = 0; e < E; ++e) lo0[e] = lo[e];
+      ParamView pv;
+      pv.mode = prm.mode;
+      pv.gauss = gauss_base ? gauss_base + (int64_t)(i / TW_PARAM_BATCH) * v.n_terms * TW_GAUSS_REC : nullptr;
+      pv.mix = mix_base;
+      TopK tk;
+      tk.n = 0;
+      int leaves = 0;
+      enumerate(v, in_s, in_e, w, lo,
+                [&](int e, int o) { return (tk_base[e][o >> 5] >> (o & 31)) & 1u; },
+                [&](const int* c, const int64_t* cs, const int64_t* ce) {
+                  if (leaves < 0x7fffffff) ++leaves;
+                  topk_offer(v, tk, score_tuple(v, pv, in_s, in_e, cs, ce), c);
+                });
+      const int64_t gi = v.in_off + i;
+      out.n_cand[gi] = leaves;
+      wb.cnt[lane] = tk.n;
+      for (int k = 0; k < tk.n; ++k) {
+        wb.score[lane][k] = tk.score[k];
+        for (int e = 0; e < E; ++e) wb.idx[lane][k][e] = tk.idx[k][e];
+      }
+      if (out.topk_score) {
+        out.topk_cnt[gi] = (uint8_t)tk.n;
+        int32_t* ix = out.topk_idx + TW_K * (v.tuple_off + (int64_t)i * E);
+        for (int k = 0; k < TW_K; ++k) {
+          out.topk_score[gi * TW_K + k] = k < tk.n ? tk.score[k] : __longlong_as_double(0x7ff8000000000000LL);
+          for (int e = 0; e < E; ++e) ix[k * E + e] = k < tk.n ? tk.idx[k][e] : -1;
+        }
+      }
+    }
+    for (int e = 0; e < E; ++e) cursor[e] = __shfl_sync(0xffffffffu, lo0[e], 0);
+    __syncwarp();
+
+    // ---- stitch the window (V3:1192-1219)
+    if (lane < nw) wb.adj[lane] = window_adjacency(wb, E, nw, lane);
+    __syncwarp();
+    long long nodes = 0;
+    if (lane == 0) nodes = mwis_solve(wb, E, nw, node_limit);
+    nodes = __shfl_sync(0xffffffffu, nodes, 0);
+    __syncwarp();
+    if (nodes < 0) { rc = TW_ERR_MWIS_LIMIT; break; }
+    if (nodes > max_nodes) max_nodes = nodes;
+    int r = -2;
+    if (lane < nw) {
+      const int i = ws + lane;
+      r = wb.chosen[lane];
+      out.mis_rank[v.in_off + i] = (int8_t)r;
+      if (r >= 0) {
+        for (int e = 0; e < E; ++e) {
+          int o = wb.idx[lane][r][e];
+          out.assign[v.tuple_off + (int64_t)e * n + i] = o;
+          atomicOr(&tk_base[e][o >> 5], 1u << (o & 31));
+        }
+      }
+    }
+    not_best += __popc(__ballot_sync(0xffffffffu, lane < nw && r != 0));
+    unassigned += __popc(__ballot_sync(0xffffffffu, lane < nw && r < 0));
+    __threadfence_block();
+    __syncwarp();
+    ws = we + 1;
+  }
+  if (lane == 0) {
+    if (rc != TW_OK) atomicMin(err_flag, rc);
+    if (out.counters) {
+      out.counters[p * 4 + 0] = not_best;
+      out.counters[p * 4 + 1] = unassigned;
+      out.counters[p * 4 + 2] = (int)(max_nodes > 0x7fffffffLL ? 0x7fffffffLL : max_nodes);
+      out.counters[p * 4 + 3] = rc;
+    }
+  }
+}
+
+cudaError_t launch_stitch(const tw_batch& b, const tw_params& prm, const uint8_t* cut,
+                          const tw_pass_out& out, uint32_t* taken_words, size_t taken_n_words,
+                          long long node_limit, int* err_flag, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(taken_words, 0, taken_n_words * sizeof(uint32_t), s);
+  if (e != cudaSuccess) return e;
+  size_t smem = sizeof(StitchWarpSmem) * kStitchWarps;
+  static bool attr_done = false;
+  if (!attr_done) {
+    e = cudaFuncSetAttribute(k_stitch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  int blocks = (b.n_problems + kStitchWarps - 1) / kStitchWarps;
+  k_stitch<<<blocks, kStitchWarps * 32, smem, s>>>(b, prm, cut, out, taken_words, node_limit, err_flag);
+  return cudaGetLastError();
+}
+
+}  // namespace tw
