@@ -71,7 +71,7 @@ struct ScoreSmem {
   OutWin win[TW_MAX_E];
   int64_t st_s[kStageSpans];
   int64_t st_e[kStageSpans];
-  double prm[TW_MAX_TERMS * TW_MIX_REC];     // mixture table, or two Gaussian batch tables
+  double prm[TW_MAX_TERMS * TW_MIX_REC];     // mixture table, or up to three Gaussian batch tables
   uint32_t used[T][TW_MAX_E][W];
   int lo_abs[T][TW_MAX_E];
   int64_t red[T / 32];
@@ -167,7 +167,8 @@ k_score(tw_batch b, tw_params prm, int has_params, tw_score_out out, TileList ti
   int batch0 = i0 / TW_PARAM_BATCH;
   if (has_params) {
     if (prm.mode == TW_PARAMS_GAUSS_BATCHED) {
-      int nrec = 2 * v.n_terms * TW_GAUSS_REC;
+      // a tile of kScoreTile (=127) in-spans can touch three 100-span batches
+      int nrec = 3 * v.n_terms * TW_GAUSS_REC;
       int nb = (n + TW_PARAM_BATCH - 1) / TW_PARAM_BATCH;
       const double* src = prm.gauss + (prm.prob_gauss_off[p] + (int64_t)batch0 * v.n_terms) * TW_GAUSS_REC;
       int avail = (nb - batch0) * v.n_terms * TW_GAUSS_REC;
