@@ -126,3 +126,21 @@ def windows_from_cuts(cut):
     ends = np.flatnonzero(we)
     starts = np.concatenate([[0], ends[:-1] + 1])
     return list(zip(starts.tolist(), ends.tolist()))
+
+
+def gmm_refit(term_sample_off, delays, counts, seed_select=10, rng_skip=None):
+    """two_gmm_refit_ex: per-term BIC-selected 1-D GMM (restated sklearn, oracle/tw_oracle_gmm.c).
+    Returns (mix[n_terms, TW_MIX_REC], n_selected, max_n)."""
+    L = lib()
+    L.two_gmm_refit_ex.restype = C.c_int
+    nt = len(counts)
+    off = np.ascontiguousarray(term_sample_off, np.int64)
+    delays = np.ascontiguousarray(delays, np.float64)
+    counts = np.ascontiguousarray(counts, np.int32)
+    mix = np.zeros((nt, _abi.TW_MIX_REC), np.float64)
+    nsel = np.zeros(nt, np.int32)
+    maxn = np.zeros(nt, np.int32)
+    skip = None if rng_skip is None else np.ascontiguousarray(rng_skip, np.uint32)
+    _check(L.two_gmm_refit_ex(C.c_int32(nt), _ptr(off), _ptr(delays), _ptr(counts), C.c_uint32(seed_select),
+                              _ptr(skip), _ptr(mix), _ptr(nsel), _ptr(maxn)), "gmm_refit")
+    return mix, nsel, maxn

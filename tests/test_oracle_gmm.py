@@ -1,0 +1,49 @@
+"""Pin the restated refit (oracle/tw_oracle_gmm.c: k-means++ / Lloyd / EM / BIC with NumPy's
+MT19937 stream) to the GaussianMixture objects the reference fitted (golden fixtures)."""
+import numpy as np
+import pytest
+
+from golden_util import Golden, golden_files
+from oracle import tw_oracle
+from traceweaver_b200 import refit
+from traceweaver_b200.batch import build_batch
+
+FILES = golden_files()
+IDS = [f.split("/")[-1][:-4] for f in FILES]
+
+
+def _setup(path):
+    g = Golden(path)
+    prob = g.problem()
+    hb = build_batch([prob])
+    ob = tw_oracle.OracleBatch(hb)
+    n, E = prob.n_in, prob.E
+    # pass-0 assignments recomputed from the golden MWIS choice
+    assign0 = np.full((E, n), -1, np.int32)
+    mis0 = g.z["mis_rank"][0]
+    idx0 = g.z["topk_idx"][0]
+    for i in range(n):
+        if mis0[i] >= 0:
+            assign0[:, i] = idx0[i, mis0[i]]
+    d_pred, c_pred = ob.delays(assign0.reshape(-1))
+    d_true, c_true = ob.delays(np.ascontiguousarray(g.z["truth"]).reshape(-1))
+    off = hb.term_sample_off
+    given_pos = [g.topo.index(ep) for ep in g.meta["out_eps_given"]]
+    skips = refit.rng_skips(prob, given_pos, refit.unique_cap(d_pred, off, c_pred),
+                            refit.unique_cap(d_true, off, c_true))
+    return g, prob, hb, d_pred, c_pred, skips
+
+
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_refit_matches_sklearn(path):
+    g, prob, hb, d_pred, c_pred, skips = _setup(path)
+    mix, nsel, _ = tw_oracle.gmm_refit(hb.term_sample_off, d_pred, c_pred, seed_select=g.meta["global_seed"],
+                                       rng_skip=skips)
+    want = g.mix_table(prob)
+    assert np.array_equal(nsel, want[:, 0].astype(np.int32)), (nsel, want[:, 0])
+    for t in range(len(nsel)):
+        k = int(nsel[t])
+        # components may come out in the same order (same seeding); compare directly
+        np.testing.assert_allclose(mix[t, 1:1 + k], want[t, 1:1 + k], rtol=1e-6)       # precision chol
+        np.testing.assert_allclose(mix[t, 6:6 + k], want[t, 6:6 + k], rtol=1e-6)       # mu * pc
+        np.testing.assert_allclose(mix[t, 16:16 + k], want[t, 16:16 + k], atol=1e-6)   # log w
