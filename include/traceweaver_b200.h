@@ -189,15 +189,29 @@ int tw_delays(tw_engine* eng, const int32_t* assign, const int64_t* term_sample_
 
 /*
  * Pass-boundary refit on the device: per term, 1-D Gaussian mixtures with 1..min(5,#unique)
- * components, BIC model selection, final full-covariance fit — the algorithm of
+ * components, BIC model selection ('diag'), final 'full' fit — the algorithm of
  * sklearn.mixture.GaussianMixture as called at traceweaver_v3.py:768-786 (k-means++ / Lloyd
- * initialisation, EM with tol 1e-3, reg_covar 1e-6, max_iter 100).  Writes TW_MIX_REC records.
- * `seed_select` seeds the model-selection fits (the reference leaves them to the unseeded global
- * NumPy RNG, v3:774), the final fit uses seed 100 (v3:784).
+ * initialisation, EM with tol 1e-3, reg_covar 1e-6, max_iter 100).  Writes n_term_total records
+ * of TW_MIX_REC doubles.  Randomness: the model-selection fits consume NumPy's GLOBAL legacy
+ * RandomState in the reference (never seeded by it, v3:774); here that stream is
+ * RandomState(seed_select), each service starts prob_base_skip[p] random_sample() calls into it
+ * (device uint32[P] or NULL = 0) and visits its terms in the order term_order (device
+ * int32[n_term_total]: global term index visited q-th, grouped by problem; NULL = term order).
+ * The final fit uses RandomState(100) (v3:784).  n_selected_out (device int32[n_term_total]) may
+ * be NULL.
  */
-int tw_gmm_refit(tw_engine* eng, int32_t n_terms, const int64_t* term_sample_off,
-                 const double* delays, const int32_t* counts, uint32_t seed_select,
-                 double* mix_out, int32_t* n_selected_out, void* stream);
+int tw_gmm_refit(tw_engine* eng, const int64_t* term_sample_off, const double* delays,
+                 const int32_t* counts, uint32_t seed_select, const uint32_t* prob_base_skip,
+                 const int32_t* term_order, double* mix_out, int32_t* n_selected_out, void* stream);
+
+/*
+ * random_sample() calls the model-selection fits of each service would consume for the given
+ * delay samples: sum over its terms of draws(min(#unique, 5)).  The reference fits GMMs on the
+ * TRUE assignments first (v3:796-818, i = 0) and discards them; they only advance the stream, so
+ * a drop-in caller feeds the truth delays here and passes the result as prob_base_skip above.
+ */
+int tw_gmm_stream_draws(tw_engine* eng, const int64_t* term_sample_off, const double* delays,
+                        const int32_t* counts, uint32_t* prob_draws_out, void* stream);
 
 #ifdef __cplusplus
 }

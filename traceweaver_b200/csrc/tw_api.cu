@@ -4,6 +4,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -53,11 +54,23 @@ struct tw_engine {
   int32_t* term_ep = nullptr;
   int32_t* ep_prob = nullptr;
   long long node_limit = 200000000LL;
+  // refit scratch (allocated on first tw_gmm_refit after bind)
+  static constexpr int kStreamLen = 16384;
+  int32_t* gmm_max_n = nullptr;
+  double* gmm_mean_var = nullptr;
+  uint32_t* gmm_skip = nullptr;
+  double* gmm_bic = nullptr;
+  double* gmm_stream = nullptr;
+  double* gmm_stream100 = nullptr;
+  uint32_t gmm_seed = 0;
+  bool gmm_seed_valid = false;
 
   void release() {
     for (void* p : owned) cudaFree(p);
     owned.clear();
     bound = false;
+    gmm_max_n = nullptr;
+    gmm_seed_valid = false;
   }
   template <class T>
   cudaError_t alloc(T** out, size_t count) {
@@ -291,9 +304,78 @@ int tw_delays(tw_engine* eng, const int32_t* assign, const int64_t* term_sample_
   return TW_OK;
 }
 
-int tw_gmm_refit(tw_engine*, int32_t, const int64_t*, const double*, const int32_t*, uint32_t, double*, int32_t*,
-                 void*) {
-  return fail(TW_ERR_UNSUPPORTED, "tw_gmm_refit: device refit not built yet (host refit via tw_delays)");
+// NumPy legacy RandomState(seed).random_sample() stream (MT19937; std::mt19937 has the same
+// init_genrand seeding and tempering): (a >> 5, b >> 6) -> (a * 2^26 + b) / 2^53.
+static void numpy_random_samples(uint32_t seed, int count, std::vector<double>& out) {
+  std::mt19937 mt(seed);
+  out.resize(count);
+  for (int i = 0; i < count; ++i) {
+    uint32_t a = (uint32_t)mt() >> 5, b = (uint32_t)mt() >> 6;
+    out[i] = (a * 67108864.0 + b) / 9007199254740992.0;
+  }
+}
+
+static int gmm_prepare(tw_engine* eng, uint32_t seed_select, cudaStream_t s) {
+  const int nt = eng->dev.n_term_total;
+  if (!eng->gmm_max_n) {
+    CU(eng->alloc(&eng->gmm_max_n, (size_t)nt));
+    CU(eng->alloc(&eng->gmm_mean_var, (size_t)nt * 2));
+    CU(eng->alloc(&eng->gmm_skip, (size_t)nt));
+    CU(eng->alloc(&eng->gmm_bic, (size_t)nt * TW_GMM_MAX_COMP));
+    CU(eng->alloc(&eng->gmm_stream, (size_t)tw_engine::kStreamLen));
+    CU(eng->alloc(&eng->gmm_stream100, 16));
+    std::vector<double> s100;
+    numpy_random_samples(100u, 16, s100);
+    CU(cudaMemcpyAsync(eng->gmm_stream100, s100.data(), 16 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));
+    eng->gmm_seed_valid = false;
+  }
+  if (!eng->gmm_seed_valid || eng->gmm_seed != seed_select) {
+    std::vector<double> st;
+    numpy_random_samples(seed_select, tw_engine::kStreamLen, st);
+    CU(cudaMemcpyAsync(eng->gmm_stream, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));
+    eng->gmm_seed = seed_select;
+    eng->gmm_seed_valid = true;
+  }
+  return TW_OK;
+}
+
+int tw_gmm_refit(tw_engine* eng, const int64_t* term_sample_off, const double* delays, const int32_t* counts,
+                 uint32_t seed_select, const uint32_t* prob_base_skip, const int32_t* term_order,
+                 double* mix_out, int32_t* n_selected_out, void* stream) {
+  int rc = need_bound(eng, "tw_gmm_refit");
+  if (rc) return rc;
+  if (!term_sample_off || !delays || !counts || !mix_out) return fail(TW_ERR_INVALID, "tw_gmm_refit: NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  rc = gmm_prepare(eng, seed_select, s);
+  if (rc) return rc;
+  const int nt = eng->dev.n_term_total;
+  CU(launch_gmm_prep(nt, term_sample_off, delays, counts, eng->gmm_max_n, eng->gmm_mean_var, s));
+  CU(launch_gmm_skip(eng->dev.n_problems, eng->dev.prob_ep_off, eng->dev.ep_term_off, term_order, eng->gmm_max_n,
+                     prob_base_skip, eng->gmm_skip, s));
+  CU(launch_gmm_fit(nt, term_sample_off, delays, counts, eng->gmm_max_n, eng->gmm_mean_var, eng->gmm_skip,
+                    eng->gmm_stream, tw_engine::kStreamLen, eng->gmm_stream100, eng->gmm_bic, mix_out,
+                    n_selected_out, eng->err_flag, s));
+  eng->launches += 4;
+  return TW_OK;
+}
+
+int tw_gmm_stream_draws(tw_engine* eng, const int64_t* term_sample_off, const double* delays,
+                        const int32_t* counts, uint32_t* prob_draws_out, void* stream) {
+  int rc = need_bound(eng, "tw_gmm_stream_draws");
+  if (rc) return rc;
+  if (!term_sample_off || !delays || !counts || !prob_draws_out)
+    return fail(TW_ERR_INVALID, "tw_gmm_stream_draws: NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  rc = gmm_prepare(eng, eng->gmm_seed_valid ? eng->gmm_seed : 10u, s);
+  if (rc) return rc;
+  const int nt = eng->dev.n_term_total;
+  CU(launch_gmm_prep(nt, term_sample_off, delays, counts, eng->gmm_max_n, eng->gmm_mean_var, s));
+  CU(launch_gmm_draws(eng->dev.n_problems, eng->dev.prob_ep_off, eng->dev.ep_term_off, eng->gmm_max_n,
+                      prob_draws_out, s));
+  eng->launches += 2;
+  return TW_OK;
 }
 
 }  // extern "C"

@@ -1,0 +1,525 @@
+// tw_gmm.cu — pass-boundary refit on the device: per score term a 1-D Gaussian mixture with
+// 1..min(5, #unique) components, BIC model selection ('diag' fits), final 'full' fit.
+//
+// Replaces ComputeEpPairDistParams5's fitting half, traceweaver_v3.py:764-786, i.e. the calls
+//     mixture.GaussianMixture(n_components=n, covariance_type='diag').fit(durations)   (x max_n)
+//     mixture.GaussianMixture(n_components=n_selected, random_state=100).fit(durations)
+// whose algorithm is scikit-learn's (k-means++ seeding + Lloyd for the initial responsibilities,
+// EM until |delta lower bound| < 1e-3, reg_covar 1e-6, n_init 1, max_iter 100), driven by
+// NumPy's legacy MT19937 stream.  The random_sample() values are data independent, so the host
+// generates the stream once (tw_api.cu) and the kernels index it.  Discrete decisions (seeding
+// draws, label assignment, stopping tests, BIC arg-min) follow the library's rules; sums are
+// warp-parallel, so parameters agree with scikit-learn to ~1e-12 relative, not bit for bit.
+//
+// Mapping: ONE WARP PER FIT, no block barriers.  A fit never stores responsibilities: each EM
+// iteration is a single sweep over the samples (32 per lane for n = 1000) that evaluates the
+// E-step and accumulates the M-step's sufficient statistics (sum r, sum r x, sum r x^2 per
+// component) in registers, reduced with shuffles.  k-means keeps no label / distance arrays
+// either: labels and closest-centre distances are recomputed from the <= 5 centres.
+//   k_gmm_prep  : warp per term      -> min(#unique, 5), mean, variance
+//   k_gmm_skip  : thread per problem -> position of every term in the model-selection stream
+//   k_gmm_bic   : warp per (term, k) -> BIC of the 'diag' fit with k components
+//   k_gmm_final : warp per term      -> arg-min BIC, 'full' fit, TW_MIX_REC record
+#include "tw_kernels.cuh"
+
+namespace tw {
+
+constexpr double kRegCovar = 1e-6;
+constexpr double kEmTol = 1e-3;
+constexpr int kEmMaxIter = 100;
+constexpr int kKmMaxIter = 300;
+constexpr double kKmTol = 1e-4;
+constexpr double kDblEps = 2.220446049250313e-16;
+constexpr int KC = TW_GMM_MAX_COMP;
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+  return v;
+}
+
+__device__ __forceinline__ int draws_for_k(int k) { return 1 + (k - 1) * (2 + (int)log((double)k)); }
+
+// _euclidean_distances(squared=True): -2 c x + c^2 + x^2, clipped at 0
+__device__ __forceinline__ double sq_dist(double c, double c2, double x, double x2) {
+  double d = dadd(dadd(dmul(-2.0, dmul(c, x)), c2), x2);
+  return d > 0.0 ? d : 0.0;
+}
+
+struct Fit {
+  double mu[KC], pc[KC], logpc[KC], logw[KC];
+};
+
+__device__ __forceinline__ int nearest(const double* cen, int k, double x) {
+  int lab = 0;
+  double best = dadd(dmul(cen[0], cen[0]), dmul(-2.0, dmul(x, cen[0])));
+#pragma unroll
+  for (int j = 1; j < KC; ++j)
+    if (j < k) {
+      double d = dadd(dmul(cen[j], cen[j]), dmul(-2.0, dmul(x, cen[j])));
+      if (d < best) { best = d; lab = j; }
+    }
+  return lab;
+}
+
+// KMeans(n_clusters=k, n_init=1).fit(X): returns the centres (on centred data) that define the
+// final labels_.  draws[] = this fit's random_sample() values.
+__device__ void kmeans_label_centers(const double* __restrict__ x, int n, int k, double mean, double tol,
+                                     const double* __restrict__ draws, double* cen_out) {
+  const int lane = threadIdx.x & 31;
+  double cen[KC];
+#pragma unroll
+  for (int j = 0; j < KC; ++j) cen[j] = 0.0;
+  // ---- k-means++ seeding.  First centre: RandomState.choice(n, p=1/n) = searchsorted(cdf, u,
+  // 'right') with cdf_i = (i+1 sequential adds of 1/n)/cdf_{n-1}: floor(u*n) unless u*n sits
+  // within rounding of an integer, in which case the sequential sum is replayed exactly.
+  {
+    double u = draws[0];
+    double un = u * (double)n;
+    int id = (int)un;
+    if (fabs(un - rint(un)) < 1e-6) {
+      double p = 1.0 / (double)n, last = 0.0, c = 0.0;
+      for (int i = 0; i < n; ++i) last += p;
+      id = n - 1;
+      for (int i = 0; i < n; ++i) { c += p; if (c / last > u) { id = i; break; } }
+    }
+    if (id > n - 1) id = n - 1;
+    cen[0] = x[id] - mean;
+  }
+  const int trials = 2 + (int)log((double)k);
+  double pot = 0.0;
+  {
+    double part = 0.0, c2 = cen[0] * cen[0];
+    for (int i = lane; i < n; i += 32) { double xi = x[i] - mean; part += sq_dist(cen[0], c2, xi, xi * xi); }
+    pot = wsum(part);
+  }
+  for (int ci = 1; ci < k; ++ci) {
+    double rv[3];
+    int cand[3];
+    for (int t = 0; t < 3; ++t) { rv[t] = t < trials ? draws[1 + (ci - 1) * trials + t] * pot : 0.0; cand[t] = n - 1; }
+    bool found[3] = {false, false, false};
+    // np.searchsorted(np.cumsum(closest), rv): first i with cumsum_i >= rv, rounds of 32 samples
+    double carry = 0.0;
+    for (int base = 0; base < n; base += 32) {
+      int i = base + lane;
+      double cl = 0.0;
+      if (i < n) {
+        double xi = x[i] - mean, x2 = xi * xi;
+        cl = sq_dist(cen[0], cen[0] * cen[0], xi, x2);
+        for (int j = 1; j < ci; ++j) { double d = sq_dist(cen[j], cen[j] * cen[j], xi, x2); cl = d < cl ? d : cl; }
+      }
+      double incl = cl;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        double o = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += o;
+      }
+      incl += carry;
+      for (int t = 0; t < trials; ++t) {
+        if (found[t]) continue;
+        unsigned m = __ballot_sync(kFull, i < n && incl >= rv[t]);
+        if (m) { cand[t] = base + __ffs(m) - 1; found[t] = true; }
+      }
+      carry = __shfl_sync(kFull, incl, 31);
+      if (found[0] && (trials < 2 || found[1]) && (trials < 3 || found[2])) break;
+    }
+    double cc[3], part[3] = {0.0, 0.0, 0.0};
+    for (int t = 0; t < 3; ++t) cc[t] = x[cand[t]] - mean;
+    for (int i = lane; i < n; i += 32) {
+      double xi = x[i] - mean, x2 = xi * xi;
+      double cl = sq_dist(cen[0], cen[0] * cen[0], xi, x2);
+      for (int j = 1; j < ci; ++j) { double d = sq_dist(cen[j], cen[j] * cen[j], xi, x2); cl = d < cl ? d : cl; }
+      for (int t = 0; t < trials; ++t) {
+        double d = sq_dist(cc[t], cc[t] * cc[t], xi, x2);
+        part[t] += d < cl ? d : cl;
+      }
+    }
+    int best = 0;
+    double bp = wsum(part[0]);
+    for (int t = 1; t < trials; ++t) {
+      double pt = wsum(part[t]);
+      if (pt < bp) { bp = pt; best = t; }
+    }
+    cen[ci] = cc[best];
+    pot = bp;
+  }
+  // ---- Lloyd (_kmeans_single_lloyd): labels are recomputed from centres, never stored
+  double prev[KC];
+#pragma unroll
+  for (int j = 0; j < KC; ++j) prev[j] = cen[j];
+  bool have_prev = false, strict = false;
+  for (int it = 0; it < kKmMaxIter; ++it) {
+    double sx[KC], cnt[KC];
+#pragma unroll
+    for (int j = 0; j < KC; ++j) { sx[j] = 0.0; cnt[j] = 0.0; }
+    bool changed = !have_prev;
+    for (int i = lane; i < n; i += 32) {
+      double xi = x[i] - mean;
+      int lab = nearest(cen, k, xi);
+      if (have_prev && nearest(prev, k, xi) != lab) changed = true;
+#pragma unroll
+      for (int j = 0; j < KC; ++j)
+        if (j == lab) { sx[j] += xi; cnt[j] += 1.0; }
+    }
+    changed = __any_sync(kFull, changed);
+#pragma unroll
+    for (int j = 0; j < KC; ++j) { sx[j] = wsum(sx[j]); cnt[j] = wsum(cnt[j]); }
+    // _relocate_empty_clusters_dense (rare): farthest point from its centre moves to the empty cluster
+    for (int j = 0; j < k; ++j) {
+      if (cnt[j] != 0.0) continue;
+      double fd = -1.0;
+      int fi = 0x7fffffff;
+      for (int i = lane; i < n; i += 32) {
+        double xi = x[i] - mean;
+        double d = xi - cen[nearest(cen, k, xi)];
+        d *= d;
+        if (d > fd) { fd = d; fi = i; }
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        double od = __shfl_xor_sync(kFull, fd, d);
+        int oi = __shfl_xor_sync(kFull, fi, d);
+        if (od > fd || (od == fd && oi < fi)) { fd = od; fi = oi; }
+      }
+      double xf = x[fi] - mean;
+      int ol = nearest(cen, k, xf);
+#pragma unroll
+      for (int q = 0; q < KC; ++q) {
+        if (q == ol) { sx[q] -= xf; cnt[q] -= 1.0; }
+        if (q == j) { sx[q] = xf; cnt[q] = 1.0; }
+      }
+    }
+    double shift_tot = 0.0;
+#pragma unroll
+    for (int j = 0; j < KC; ++j) {
+      prev[j] = cen[j];
+      if (j < k) {
+        double nc = cnt[j] > 0.0 ? sx[j] * (1.0 / cnt[j]) : sx[j];
+        double d = fabs(nc - cen[j]);
+        shift_tot += d * d;
+        cen[j] = nc;
+      }
+    }
+    have_prev = true;
+    if (!changed) { strict = true; break; }
+    if (shift_tot <= tol) break;
+  }
+  // strict convergence keeps the labels of the last assignment (w.r.t. the centres before the
+  // final update); otherwise sklearn re-runs the assignment with the final centres
+#pragma unroll
+  for (int j = 0; j < KC; ++j) cen_out[j] = strict ? prev[j] : cen[j];
+}
+
+// parameters from sufficient statistics S0 = sum r, S1 = sum r x', S2 = sum r x'^2 where
+// x' = x - shift ('full': shift = sample mean, keeps the one-pass variance well conditioned;
+// 'diag': shift = 0, which IS scikit-learn's avg_X2 - means^2 formula).
+__device__ __forceinline__ bool params_from_stats(Fit& f, int k, int n, const double* S0, const double* S1,
+                                                  const double* S2, double shift, bool init) {
+  double nk[KC], tot = 0.0;
+  bool ok = true;
+#pragma unroll
+  for (int c = 0; c < KC; ++c) {
+    nk[c] = S0[c] + 10.0 * kDblEps;
+    if (c < k) tot += nk[c];
+  }
+#pragma unroll
+  for (int c = 0; c < KC; ++c) {
+    if (c < k) {
+      double m = S1[c] / nk[c];
+      double cov = S2[c] / nk[c] - m * m + kRegCovar;
+      if (!(cov > 0.0)) ok = false;
+      f.mu[c] = m + shift;
+      f.pc[c] = 1.0 / sqrt(cov);
+      f.logpc[c] = log(f.pc[c]);
+      f.logw[c] = log(init ? nk[c] / (double)n : nk[c] / tot);
+    }
+  }
+  return ok;
+}
+
+// weighted log-probabilities of one sample (sklearn _estimate_log_gaussian_prob + log weights)
+// and their logsumexp
+template <bool FULL>
+__device__ __forceinline__ double estep(const Fit& f, int k, double x, double* a) {
+  double amax = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < KC; ++c) {
+    if (c < k) {
+      double lp;
+      if (FULL) {
+        double y = dsub(dmul(x, f.pc[c]), dmul(f.mu[c], f.pc[c]));
+        lp = dmul(y, y);
+      } else {
+        double prec = dmul(f.pc[c], f.pc[c]);
+        lp = dadd(dsub(dmul(dmul(f.mu[c], f.mu[c]), prec), dmul(2.0, dmul(x, dmul(f.mu[c], prec)))),
+                  dmul(dmul(x, x), prec));
+      }
+      a[c] = dadd(dadd(dmul(-0.5, dadd(TW_LOG_2PI, lp)), f.logpc[c]), f.logw[c]);
+      amax = a[c] > amax ? a[c] : amax;
+    }
+  }
+  double s = 0.0, m = 0.0;
+#pragma unroll
+  for (int c = 0; c < KC; ++c) {
+    if (c < k) {
+      if (a[c] == amax) m += 1.0;
+      else s += exp(a[c] - amax);
+    }
+  }
+  if (m > 1.0) return log1p(s / m) + log(m) + amax;
+  return log1p(s) + amax;
+}
+
+// GaussianMixture(k, covariance_type = FULL ? 'full' : 'diag').fit(x) by one warp.
+// Returns false on scikit-learn's ValueError paths; *score = mean log-likelihood under the final
+// parameters when want_score.
+template <bool FULL>
+__device__ bool warp_fit(const double* __restrict__ x, int n, int k, double mean, double tol,
+                         const double* __restrict__ draws, Fit& f, bool want_score, double* score) {
+  const int lane = threadIdx.x & 31;
+  if (n < 2 || n < k) return false;
+  const double shift = FULL ? mean : 0.0;
+  double S0[KC], S1[KC], S2[KC];
+  {
+    double cen[KC];
+    kmeans_label_centers(x, n, k, mean, tol, draws, cen);
+#pragma unroll
+    for (int c = 0; c < KC; ++c) { S0[c] = 0.0; S1[c] = 0.0; S2[c] = 0.0; }
+    for (int i = lane; i < n; i += 32) {
+      double xi = x[i];
+      int lab = nearest(cen, k, xi - mean);
+      double xs = xi - shift;
+#pragma unroll
+      for (int c = 0; c < KC; ++c)
+        if (c == lab) { S0[c] += 1.0; S1[c] += xs; S2[c] += xs * xs; }
+    }
+#pragma unroll
+    for (int c = 0; c < KC; ++c) { S0[c] = wsum(S0[c]); S1[c] = wsum(S1[c]); S2[c] = wsum(S2[c]); }
+  }
+  if (!params_from_stats(f, k, n, S0, S1, S2, shift, true)) return false;
+  double lower = -INFINITY;
+  for (int it = 1; it <= kEmMaxIter; ++it) {
+    double prev = lower, part = 0.0;
+#pragma unroll
+    for (int c = 0; c < KC; ++c) { S0[c] = 0.0; S1[c] = 0.0; S2[c] = 0.0; }
+    for (int i = lane; i < n; i += 32) {
+      double xi = x[i], a[KC];
+      double l = estep<FULL>(f, k, xi, a);
+      part += l;
+      double xs = xi - shift;
+#pragma unroll
+      for (int c = 0; c < KC; ++c)
+        if (c < k) {
+          double r = exp(a[c] - l);
+          S0[c] += r; S1[c] += r * xs; S2[c] += r * (xs * xs);
+        }
+    }
+    lower = wsum(part) / (double)n;
+#pragma unroll
+    for (int c = 0; c < KC; ++c) { S0[c] = wsum(S0[c]); S1[c] = wsum(S1[c]); S2[c] = wsum(S2[c]); }
+    if (!params_from_stats(f, k, n, S0, S1, S2, shift, false)) return false;
+    if (fabs(lower - prev) < kEmTol) break;
+  }
+  if (want_score) {
+    double part = 0.0;
+    for (int i = lane; i < n; i += 32) { double a[KC]; part += estep<FULL>(f, k, x[i], a); }
+    *score = wsum(part) / (double)n;
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-term statistics: min(#unique, 5) (V3:768), mean, variance
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_gmm_prep(int n_terms, const int64_t* __restrict__ term_sample_off, const double* __restrict__ delays,
+           const int32_t* __restrict__ counts, int32_t* __restrict__ max_n, double* __restrict__ mean_var) {
+  const int t = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= n_terms) return;
+  const double* x = delays + term_sample_off[t];
+  const int n = counts[t];
+  double set[KC];
+  int ns = 0;
+  double part = 0.0;
+  for (int i = lane; i < n; i += 32) {
+    double v = x[i];
+    part += v;
+    bool seen = false;
+#pragma unroll
+    for (int q = 0; q < KC; ++q)
+      if (q < ns && set[q] == v) seen = true;
+    if (!seen && ns < KC) {
+#pragma unroll
+      for (int q = 0; q < KC; ++q)
+        if (q == ns) set[q] = v;
+      ++ns;
+    }
+  }
+  // merge the lanes' small sets on lane 0's view (all lanes run the same merge)
+  double mset[KC];
+  int mn = 0;
+  for (int src = 0; src < 32 && mn < KC; ++src) {
+    int sn = __shfl_sync(kFull, ns, src);
+    for (int q = 0; q < KC; ++q) {
+      double v = __shfl_sync(kFull, set[q < KC ? q : 0], src);
+      if (q >= sn || mn >= KC) continue;
+      bool seen = false;
+#pragma unroll
+      for (int r = 0; r < KC; ++r)
+        if (r < mn && mset[r] == v) seen = true;
+      if (!seen) {
+#pragma unroll
+        for (int r = 0; r < KC; ++r)
+          if (r == mn) mset[r] = v;
+        ++mn;
+      }
+    }
+  }
+  double mean = n > 0 ? wsum(part) / (double)n : 0.0;
+  double p2 = 0.0;
+  for (int i = lane; i < n; i += 32) { double d = x[i] - mean; p2 += d * d; }
+  double var = n > 0 ? wsum(p2) / (double)n : 0.0;
+  if (lane == 0) {
+    max_n[t] = n > 0 ? mn : 0;
+    mean_var[2 * t] = mean;
+    mean_var[2 * t + 1] = var;
+  }
+}
+
+// position of every term in the model-selection random stream: the reference fits the terms of a
+// service one after the other (order = term_rank) from ONE stream, after the fits on the true
+// assignments (prob_base_skip[p] draws, 0 when there is no truth pass).
+__global__ void k_gmm_skip(int n_problems, const int32_t* __restrict__ prob_ep_off,
+                           const int32_t* __restrict__ ep_term_off, const int32_t* __restrict__ term_order,
+                           const int32_t* __restrict__ max_n, const uint32_t* __restrict__ prob_base_skip,
+                           uint32_t* __restrict__ rng_skip) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_problems) return;
+  int t0 = ep_term_off[prob_ep_off[p]], t1 = ep_term_off[prob_ep_off[p + 1]];
+  uint32_t pos = prob_base_skip ? prob_base_skip[p] : 0u;
+  for (int q = t0; q < t1; ++q) {
+    int t = term_order ? term_order[q] : q;   // global term index visited q-th
+    rng_skip[t] = pos;
+    int mn = max_n[t];
+    for (int k = 1; k <= mn; ++k) pos += (uint32_t)draws_for_k(k);
+  }
+}
+
+// draws the model-selection fits of each problem consume (truth pass bookkeeping)
+__global__ void k_gmm_draws(int n_problems, const int32_t* __restrict__ prob_ep_off,
+                            const int32_t* __restrict__ ep_term_off, const int32_t* __restrict__ max_n,
+                            uint32_t* __restrict__ prob_draws) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_problems) return;
+  uint32_t pos = 0;
+  for (int t = ep_term_off[prob_ep_off[p]]; t < ep_term_off[prob_ep_off[p + 1]]; ++t)
+    for (int k = 1; k <= max_n[t]; ++k) pos += (uint32_t)draws_for_k(k);
+  prob_draws[p] = pos;
+}
+
+__global__ void __launch_bounds__(128)
+k_gmm_bic(int n_terms, const int64_t* __restrict__ term_sample_off, const double* __restrict__ delays,
+          const int32_t* __restrict__ counts, const int32_t* __restrict__ max_n,
+          const double* __restrict__ mean_var, const uint32_t* __restrict__ rng_skip,
+          const double* __restrict__ stream, int stream_len, double* __restrict__ bic_out,
+          int* __restrict__ err_flag) {
+  const int wid = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (wid >= n_terms * KC) return;
+  const int t = wid / KC, k = wid % KC + 1;
+  const int lane = threadIdx.x & 31;
+  double bic = INFINITY;
+  const int n = counts[t];
+  if (k <= max_n[t]) {
+    uint32_t pos = rng_skip[t];
+    for (int q = 1; q < k; ++q) pos += (uint32_t)draws_for_k(q);
+    if ((int)pos + draws_for_k(k) > stream_len) {
+      if (lane == 0) atomicMin(err_flag, (int)TW_ERR_RANGE_LIMIT);
+    } else {
+      Fit f;
+      double sc = 0.0;
+      const double* x = delays + term_sample_off[t];
+      if (warp_fit<false>(x, n, k, mean_var[2 * t], mean_var[2 * t + 1] * kKmTol, stream + pos, f, true, &sc))
+        bic = -2.0 * sc * (double)n + (double)(3 * k - 1) * log((double)n);   // GaussianMixture.bic, 'diag'
+    }
+  }
+  if (lane == 0) bic_out[(size_t)t * KC + (k - 1)] = bic;
+}
+
+__global__ void __launch_bounds__(128)
+k_gmm_final(int n_terms, const int64_t* __restrict__ term_sample_off, const double* __restrict__ delays,
+            const int32_t* __restrict__ counts, const int32_t* __restrict__ max_n,
+            const double* __restrict__ mean_var, const double* __restrict__ bic,
+            const double* __restrict__ stream100, double* __restrict__ mix_out,
+            int32_t* __restrict__ n_selected_out) {
+  const int t = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (t >= n_terms) return;
+  const int lane = threadIdx.x & 31;
+  const int n = counts[t];
+  int best_k = 0;
+  double best = INFINITY;
+  for (int k = 1; k <= max_n[t]; ++k) {     // np.argmin over the fits that did not raise: first minimum
+    double b = bic[(size_t)t * KC + (k - 1)];
+    if (b < best) { best = b; best_k = k; }
+  }
+  Fit f;
+  bool ok = false;
+  if (best_k > 0)
+    ok = warp_fit<true>(delays + term_sample_off[t], n, best_k, mean_var[2 * t], mean_var[2 * t + 1] * kKmTol,
+                        stream100, f, false, nullptr);
+  if (lane == 0) {
+    double* rec = mix_out + (size_t)t * TW_MIX_REC;
+    for (int q = 0; q < TW_MIX_REC; ++q) rec[q] = 0.0;
+    if (ok) {
+      rec[0] = (double)best_k;
+      for (int c = 0; c < best_k; ++c) {
+        rec[1 + c] = f.pc[c];
+        rec[6 + c] = f.mu[c] * f.pc[c];
+        rec[11 + c] = f.logpc[c];
+        rec[16 + c] = f.logw[c];
+      }
+    } else {   // no samples / no fit: services_times = (0, 0) -> sigma clamp (V3:765-766, V1:130-131)
+      rec[2] = 0.001;
+      rec[3] = log(0.001);
+    }
+    if (n_selected_out) n_selected_out[t] = ok ? best_k : 0;
+  }
+}
+
+cudaError_t launch_gmm_prep(int n_terms, const int64_t* term_sample_off, const double* delays,
+                            const int32_t* counts, int32_t* max_n, double* mean_var, cudaStream_t s) {
+  k_gmm_prep<<<(n_terms + 3) / 4, 128, 0, s>>>(n_terms, term_sample_off, delays, counts, max_n, mean_var);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gmm_skip(int n_problems, const int32_t* prob_ep_off, const int32_t* ep_term_off,
+                            const int32_t* term_order, const int32_t* max_n, const uint32_t* prob_base_skip,
+                            uint32_t* rng_skip, cudaStream_t s) {
+  k_gmm_skip<<<(n_problems + 127) / 128, 128, 0, s>>>(n_problems, prob_ep_off, ep_term_off, term_order, max_n,
+                                                       prob_base_skip, rng_skip);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gmm_draws(int n_problems, const int32_t* prob_ep_off, const int32_t* ep_term_off,
+                             const int32_t* max_n, uint32_t* prob_draws, cudaStream_t s) {
+  k_gmm_draws<<<(n_problems + 127) / 128, 128, 0, s>>>(n_problems, prob_ep_off, ep_term_off, max_n, prob_draws);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gmm_fit(int n_terms, const int64_t* term_sample_off, const double* delays,
+                           const int32_t* counts, const int32_t* max_n, const double* mean_var,
+                           const uint32_t* rng_skip, const double* stream, int stream_len,
+                           const double* stream100, double* bic, double* mix_out, int32_t* n_selected_out,
+                           int* err_flag, cudaStream_t s) {
+  int warps = n_terms * KC;
+  k_gmm_bic<<<(warps + 3) / 4, 128, 0, s>>>(n_terms, term_sample_off, delays, counts, max_n, mean_var, rng_skip,
+                                            stream, stream_len, bic, err_flag);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  k_gmm_final<<<(n_terms + 3) / 4, 128, 0, s>>>(n_terms, term_sample_off, delays, counts, max_n, mean_var, bic,
+                                                stream100, mix_out, n_selected_out);
+  return cudaGetLastError();
+}
+
+}  // namespace tw

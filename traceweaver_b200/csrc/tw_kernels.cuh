@@ -46,4 +46,17 @@ cudaError_t launch_delays(const tw_batch& b, const int32_t* assign, const int64_
                           const int32_t* term_ep, const int32_t* ep_prob, double* delays,
                           int32_t* counts, cudaStream_t s);
 
+cudaError_t launch_gmm_prep(int n_terms, const int64_t* term_sample_off, const double* delays,
+                            const int32_t* counts, int32_t* max_n, double* mean_var, cudaStream_t s);
+cudaError_t launch_gmm_skip(int n_problems, const int32_t* prob_ep_off, const int32_t* ep_term_off,
+                            const int32_t* term_order, const int32_t* max_n,
+                            const uint32_t* prob_base_skip, uint32_t* rng_skip, cudaStream_t s);
+cudaError_t launch_gmm_draws(int n_problems, const int32_t* prob_ep_off, const int32_t* ep_term_off,
+                             const int32_t* max_n, uint32_t* prob_draws, cudaStream_t s);
+cudaError_t launch_gmm_fit(int n_terms, const int64_t* term_sample_off, const double* delays,
+                           const int32_t* counts, const int32_t* max_n, const double* mean_var,
+                           const uint32_t* rng_skip, const double* stream, int stream_len,
+                           const double* stream100, double* bic, double* mix_out,
+                           int32_t* n_selected_out, int* err_flag, cudaStream_t s);
+
 }  // namespace tw

@@ -152,6 +152,24 @@ class Engine:
         _lib.check(self.lib.tw_stitch(self.h, C.byref(ps), _p(cut), C.byref(s), self.stream), "tw_stitch")
         return out
 
+    def gmm_refit(self, delays, counts, seed_select=10, prob_base_skip=None, term_order=None, want_selected=False):
+        """tw_gmm_refit: BIC-selected 1-D GMM per term on the device -> mixture Params."""
+        nt = int(self.hb.ep_term_off[-1])
+        mix = torch.empty((nt, _abi.TW_MIX_REC), dtype=torch.float64, device=self.device)
+        nsel = torch.empty(nt, dtype=torch.int32, device=self.device) if want_selected else None
+        _lib.check(self.lib.tw_gmm_refit(self.h, _p(self.d["term_sample_off"]), _p(delays), _p(counts),
+                                         C.c_uint32(seed_select), _p(prob_base_skip), _p(term_order), _p(mix),
+                                         _p(nsel), self.stream), "tw_gmm_refit")
+        prm = Params(_abi.TW_PARAMS_MIXTURE, mix, self.d["prob_gauss_off"])
+        return (prm, nsel) if want_selected else prm
+
+    def gmm_stream_draws(self, delays, counts):
+        """tw_gmm_stream_draws: per-problem random_sample() consumption of a model-selection pass."""
+        out = torch.empty(self.hb.n_problems, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.tw_gmm_stream_draws(self.h, _p(self.d["term_sample_off"]), _p(delays), _p(counts),
+                                                _p(out), self.stream), "tw_gmm_stream_draws")
+        return out
+
     def delays(self, assign):
         hb = self.hb
         delays = torch.empty(int(hb.term_sample_off[-1]), dtype=torch.float64, device=self.device)

@@ -1,0 +1,136 @@
+"""Drop-in predictor: the reference's plugin interface for the accelerated path.
+
+Mirrors `TraceWeaverV3` of the reference (src/trace_reconstructor/ports/python/algorithms/
+traceweaver_v3.py:29, constructed as `Cls(all_spans, all_processes)` and registered in
+executor.py:888-900) for method "MaxScoreBatchSubsetWithSkips": same constructor, same
+`FindAssignments` signature (traceweaver_v3.py:1087), same 6-tuple result (:1229), so the
+reference's executor.py and helpers/utils.py accuracy code run unmodified on top of it (see
+INTEGRATION.md).  All compute is in the CUDA engine behind the C ABI; this file only marshals
+`Span` objects to SoA arrays and index results back to span ids.
+"""
+import numpy as np
+import torch
+
+from . import _abi, refit
+from .batch import Problem, build_batch
+from .engine import Engine
+
+METHOD = "MaxScoreBatchSubsetWithSkips"
+NA = ("NA", "NA")
+
+
+def solve_batch(eng: Engine, hb, seed_select=10, truth_assign=None, term_order=None, device_arrays=None,
+                pinned=False, keep=("assign", "mis_rank", "counters", "n_cand", "topk")):
+    """The whole path for a bound-able batch: both passes of traceweaver_v3.py:1159-1227.
+
+    params0 -> windows -> stitch (pass 0) -> delays -> refit -> score (final top-K) -> stitch
+    (pass 1).  Returns device tensors; one host sync at the end (engine status)."""
+    eng.bind(hb, device_arrays=device_arrays, pinned=pinned)
+    p0 = eng.params_pass0()                       # ComputeEpPairDistParams3, every 100-span batch
+    sc = eng.score()                              # CreateWindows2: perfect-cut flags
+    r0 = eng.stitch(p0, sc["cut"])                # iteration 0
+    delays, counts = eng.delays(r0["assign"])     # ComputeEpPairDistParams5: durations
+    base = None
+    if truth_assign is not None:
+        # the reference fits (and discards) GMMs on the TRUE assignments first; they only advance
+        # NumPy's global random stream
+        dt, ct = eng.delays(truth_assign)
+        base = eng.gmm_stream_draws(dt, ct)
+    p1 = eng.gmm_refit(delays, counts, seed_select=seed_select, prob_base_skip=base, term_order=term_order)
+    top = eng.score(p1)                           # top_k_2 of the last iteration -> all_topk_assignments
+    r1 = eng.stitch(p1, sc["cut"])                # iteration 1
+    n_cand = r0["n_cand"] + r1["n_cand"]          # per_span_candidates accumulates over iterations
+    eng.status()
+    return dict(assign=r1["assign"], mis_rank=r1["mis_rank"], counters=r1["counters"], n_cand=n_cand,
+                topk_score=top["topk_score"], topk_idx=top["topk_idx"], topk_cnt=top["topk_cnt"],
+                cut=sc["cut"], params_pass1=p1, assign_pass0=r0["assign"])
+
+
+class TraceWeaverV3:
+    """`predictors` entry replacing the reference's ("MaxScoreBatchSubsetWithSkips", TraceWeaverV3)."""
+
+    def __init__(self, all_spans, all_processes, device=0, seed_select=10):
+        self.all_spans = all_spans
+        self.all_processes = all_processes
+        self.seed_select = seed_select
+        self.engine = Engine(device)          # raises without a CUDA device: there is no CPU path
+        self.last = None
+
+    # -- marshalling -------------------------------------------------------------------------------
+    @staticmethod
+    def _arrays(spans):
+        s = np.fromiter((sp.start_mus for sp in spans), np.int64, len(spans))
+        d = np.fromiter((sp.duration_mus for sp in spans), np.int64, len(spans))
+        return s, s + d
+
+    def _problem(self, process, in_spans, out_span_partitions, invocation_graph):
+        import networkx as nx
+        out_eps = list(nx.topological_sort(invocation_graph))            # traceweaver_v1.py:37-39
+        if set(out_eps) != set(out_span_partitions.keys()):
+            raise ValueError("invocation_graph nodes must be the outgoing endpoints")
+        pos = {ep: i for i, ep in enumerate(out_eps)}
+        in_s, in_e = self._arrays(in_spans)
+        outs = [self._arrays(out_span_partitions[ep]) for ep in out_eps]
+        preds = [[pos[b] for b, _ in invocation_graph.in_edges(ep)] for ep in out_eps]
+        prob = Problem(in_start=in_s, in_end=in_e, out_start=[o[0] for o in outs], out_end=[o[1] for o in outs],
+                       preds=preds, name=process)
+        return prob, out_eps
+
+    # -- the reference's entry point ---------------------------------------------------------------
+    def FindAssignments(self, method, process, in_span_partitions, out_span_partitions, parallel,
+                        instrumented_hops, true_assignments, invocation_graph, true_skips=False,
+                        true_dist=False):
+        assert len(in_span_partitions) == 1                              # traceweaver_v3.py:1088
+        if method != METHOD or true_skips or true_dist:
+            raise NotImplementedError(
+                f"traceweaver_b200 accelerates method {METHOD!r} only (got {method!r}); the ablation "
+                "variants stay with the reference implementation")
+        in_ep, in_spans = list(in_span_partitions.items())[0]
+        # TallySkipSpans re-sorts every partition by start (stable), traceweaver_v3.py:968-971
+        in_spans = sorted(in_spans, key=lambda x: float(x.start_mus))
+        out_parts = {ep: sorted(p, key=lambda x: float(x.start_mus)) for ep, p in out_span_partitions.items()}
+        for ep, p in out_parts.items():
+            if len(p) != len(in_spans):
+                raise NotImplementedError(
+                    f"endpoint {ep!r}: {len(p)} outgoing vs {len(in_spans)} incoming spans — skip budgets "
+                    "(cache hits / dynamism, SURVEY.md §8 row f-4) are not built; use the reference for them")
+        prob, out_eps = self._problem(process, in_spans, out_parts, invocation_graph)
+        hb = build_batch([prob])
+        n, E = prob.n_in, prob.E
+
+        in_ids = [s.GetId() for s in in_spans]
+        out_ids = [[s.GetId() for s in out_parts[ep]] for ep in out_eps]
+        # ground truth only advances the refit's random stream, exactly as in the reference
+        truth = np.full((E, n), -1, np.int32)
+        for e, ep in enumerate(out_eps):
+            lut = {sid: j for j, sid in enumerate(out_ids[e])}
+            ta = true_assignments.get(ep, {}) if true_assignments else {}
+            truth[e] = [lut.get(ta.get(i), -1) for i in in_ids]
+        given_pos = [out_eps.index(ep) for ep in out_span_partitions.keys()]
+        order = np.asarray(refit.reference_term_order(prob, given_pos), np.int32)
+
+        dev = self.engine.device
+        res = solve_batch(self.engine, hb, seed_select=self.seed_select,
+                          truth_assign=torch.from_numpy(truth.reshape(-1)).to(dev),
+                          term_order=torch.from_numpy(order).to(dev))
+        self.last = res
+        assign = res["assign"].cpu().numpy().reshape(E, n)
+        topk_idx = res["topk_idx"].cpu().numpy().reshape(n, _abi.TW_K, E)
+        topk_cnt = res["topk_cnt"].cpu().numpy()
+        n_cand = res["n_cand"].cpu().numpy()
+        counters = res["counters"].cpu().numpy()
+
+        all_assignments, all_topk = {}, {}
+        for e, ep in enumerate(out_eps):
+            ids = out_ids[e]
+            col = assign[e]
+            all_assignments[ep] = {in_ids[i]: (ids[col[i]] if col[i] >= 0 else NA) for i in range(n)}
+            all_topk[ep] = {in_ids[i]: [ids[topk_idx[i, r, e]] for r in range(topk_cnt[i])] for i in range(n)}
+        per_span_candidates = {}
+        for ep in out_span_partitions.keys():                            # traceweaver_v3.py:1096-1098
+            for key in (true_assignments.get(ep, {}) if true_assignments else {}):
+                per_span_candidates[key] = 0
+        for i in range(n):
+            if n_cand[i] or in_ids[i] in per_span_candidates:
+                per_span_candidates[in_ids[i]] = int(n_cand[i])
+        return (all_assignments, all_topk, int(counters[0, 0]), n, per_span_candidates, int(counters[0, 1]))
