@@ -211,25 +211,25 @@ __device__ void kmeans_label_centers(const double* __restrict__ x, int n, int k,
   for (int j = 0; j < KC; ++j) cen_out[j] = strict ? prev[j] : cen[j];
 }
 
-// parameters from sufficient statistics S0 = sum r, S1 = sum r x', S2 = sum r x'^2 where
-// x' = x - shift ('full': shift = sample mean, keeps the one-pass variance well conditioned;
-// 'diag': shift = 0, which IS scikit-learn's avg_X2 - means^2 formula).
-__device__ __forceinline__ bool params_from_stats(Fit& f, int k, int n, const double* S0, const double* S1,
+// parameters from the M-step sums.  S0 = sum r, S1 = sum r x' (x' = x - shift).
+//   'diag': S2 = sum r x^2 with shift = 0 and cov = S2/nk - mu^2 + reg — scikit-learn's own
+//           avg_X2 - means^2 formula (_estimate_gaussian_covariances_diag);
+//   'full': S2 = sum r (x' - mu')^2 from a second sweep (_estimate_gaussian_covariances_full),
+//           so a component of identical samples gets cov = reg_covar exactly, as in the library.
+template <bool FULL>
+__device__ __forceinline__ bool params_from_stats(Fit& f, int k, int n, const double* nk, const double* mup,
                                                   const double* S2, double shift, bool init) {
-  double nk[KC], tot = 0.0;
+  double tot = 0.0;
   bool ok = true;
 #pragma unroll
-  for (int c = 0; c < KC; ++c) {
-    nk[c] = S0[c] + 10.0 * kDblEps;
+  for (int c = 0; c < KC; ++c)
     if (c < k) tot += nk[c];
-  }
 #pragma unroll
   for (int c = 0; c < KC; ++c) {
     if (c < k) {
-      double m = S1[c] / nk[c];
-      double cov = S2[c] / nk[c] - m * m + kRegCovar;
+      double cov = FULL ? S2[c] / nk[c] + kRegCovar : S2[c] / nk[c] - mup[c] * mup[c] + kRegCovar;
       if (!(cov > 0.0)) ok = false;
-      f.mu[c] = m + shift;
+      f.mu[c] = mup[c] + shift;
       f.pc[c] = 1.0 / sqrt(cov);
       f.logpc[c] = log(f.pc[c]);
       f.logw[c] = log(init ? nk[c] / (double)n : nk[c] / tot);
@@ -280,7 +280,7 @@ __device__ bool warp_fit(const double* __restrict__ x, int n, int k, double mean
   const int lane = threadIdx.x & 31;
   if (n < 2 || n < k) return false;
   const double shift = FULL ? mean : 0.0;
-  double S0[KC], S1[KC], S2[KC];
+  double S0[KC], S1[KC], S2[KC], nk[KC], mup[KC];
   {
     double cen[KC];
     kmeans_label_centers(x, n, k, mean, tol, draws, cen);
@@ -295,9 +295,27 @@ __device__ bool warp_fit(const double* __restrict__ x, int n, int k, double mean
         if (c == lab) { S0[c] += 1.0; S1[c] += xs; S2[c] += xs * xs; }
     }
 #pragma unroll
-    for (int c = 0; c < KC; ++c) { S0[c] = wsum(S0[c]); S1[c] = wsum(S1[c]); S2[c] = wsum(S2[c]); }
+    for (int c = 0; c < KC; ++c) {
+      nk[c] = wsum(S0[c]) + 10.0 * kDblEps;
+      mup[c] = wsum(S1[c]) / nk[c];
+      S2[c] = wsum(S2[c]);
+    }
+    if (FULL) {   // second sweep: sum of squared deviations from the new means
+#pragma unroll
+      for (int c = 0; c < KC; ++c) S2[c] = 0.0;
+      for (int i = lane; i < n; i += 32) {
+        double xi = x[i];
+        int lab = nearest(cen, k, xi - mean);
+        double xs = xi - shift;
+#pragma unroll
+        for (int c = 0; c < KC; ++c)
+          if (c == lab) { double d = xs - mup[c]; S2[c] += d * d; }
+      }
+#pragma unroll
+      for (int c = 0; c < KC; ++c) S2[c] = wsum(S2[c]);
+    }
   }
-  if (!params_from_stats(f, k, n, S0, S1, S2, shift, true)) return false;
+  if (!params_from_stats<FULL>(f, k, n, nk, mup, S2, shift, true)) return false;
   double lower = -INFINITY;
   for (int it = 1; it <= kEmMaxIter; ++it) {
     double prev = lower, part = 0.0;
@@ -312,13 +330,32 @@ __device__ bool warp_fit(const double* __restrict__ x, int n, int k, double mean
       for (int c = 0; c < KC; ++c)
         if (c < k) {
           double r = exp(a[c] - l);
-          S0[c] += r; S1[c] += r * xs; S2[c] += r * (xs * xs);
+          S0[c] += r; S1[c] += r * xs;
+          if (!FULL) S2[c] += r * (xs * xs);
         }
     }
     lower = wsum(part) / (double)n;
 #pragma unroll
-    for (int c = 0; c < KC; ++c) { S0[c] = wsum(S0[c]); S1[c] = wsum(S1[c]); S2[c] = wsum(S2[c]); }
-    if (!params_from_stats(f, k, n, S0, S1, S2, shift, false)) return false;
+    for (int c = 0; c < KC; ++c) {
+      nk[c] = wsum(S0[c]) + 10.0 * kDblEps;
+      mup[c] = wsum(S1[c]) / nk[c];
+      if (!FULL) S2[c] = wsum(S2[c]);
+    }
+    if (FULL) {   // responsibilities under the OLD parameters, deviations from the NEW means
+#pragma unroll
+      for (int c = 0; c < KC; ++c) S2[c] = 0.0;
+      for (int i = lane; i < n; i += 32) {
+        double xi = x[i], a[KC];
+        double l = estep<FULL>(f, k, xi, a);
+        double xs = xi - shift;
+#pragma unroll
+        for (int c = 0; c < KC; ++c)
+          if (c < k) { double d = xs - mup[c]; S2[c] += (exp(a[c] - l) * d) * d; }
+      }
+#pragma unroll
+      for (int c = 0; c < KC; ++c) S2[c] = wsum(S2[c]);
+    }
+    if (!params_from_stats<FULL>(f, k, n, nk, mup, S2, shift, false)) return false;
     if (fabs(lower - prev) < kEmTol) break;
   }
   if (want_score) {
