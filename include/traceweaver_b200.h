@@ -141,11 +141,17 @@ int tw_batch_validate_host(const tw_batch* host_desc);
  * Bind a batch.  `dev` holds DEVICE pointers (all fields); `host_desc` holds HOST copies of the
  * descriptor arrays (prob_*, ep_*, term_src; its span pointers are ignored).  Validates the
  * descriptors (the asserts of v3:1088,1198 plus engine limits), rejects skip budgets
- * (n_out != n_in -> TW_ERR_UNSUPPORTED), builds the tile lists and allocates scratch, and runs the
- * batch-constant pre-kernels (prev-index scan for PerfectCut v3:1026-1032, sorted end times for
- * v3:624-645).  The arrays behind `dev` must stay alive and unchanged while bound.
+ * (n_out != n_in -> TW_ERR_UNSUPPORTED), builds the tile lists and (re)uses grow-only device scratch.
+ * The arrays behind `dev` must stay alive and unchanged while bound.
  */
 int tw_engine_bind(tw_engine* eng, const tw_batch* dev, const tw_batch* host_desc, void* stream);
+
+/*
+ * Batch-constant pre-kernels of the path, once per bound batch before the first pass: the
+ * prev-index scan PerfectCut walks (v3:1026-1032) and the sorted end-time arrays the pass-0
+ * order statistics read (v3:624-645; start times arrive sorted, end times do not).
+ */
+int tw_prepare(tw_engine* eng, void* stream);
 
 /* Blocks until `stream` is idle and returns the sticky device-side status of the kernels
  * launched since the last call (TW_OK, TW_ERR_MWIS_LIMIT, TW_ERR_RANGE_LIMIT, ...). */

@@ -144,3 +144,26 @@ def gmm_refit(term_sample_off, delays, counts, seed_select=10, rng_skip=None):
     _check(L.two_gmm_refit_ex(C.c_int32(nt), _ptr(off), _ptr(delays), _ptr(counts), C.c_uint32(seed_select),
                               _ptr(skip), _ptr(mix), _ptr(nsel), _ptr(maxn)), "gmm_refit")
     return mix, nsel, maxn
+
+
+def find_assignments(hb: HostBatch, seed_select=10, threads=1, want_topk=True):
+    """two_find_assignments: the whole restated path over a batch on `threads` host threads."""
+    L = lib()
+    L.two_find_assignments.restype = C.c_int
+    n, nt = int(hb.prob_in_off[-1]), int(hb.prob_tuple_off[-1])
+    nterm = int(hb.ep_term_off[-1])
+    res = dict(assign=np.full(nt, -1, np.int32), mis_rank=np.full(n, -1, np.int8), n_cand=np.zeros(n, np.int32),
+               counters=np.zeros((hb.n_problems, 4), np.int32), n_cand_total=np.zeros(n, np.int32),
+               mix=np.zeros((nterm, _abi.TW_MIX_REC)))
+    if want_topk:
+        res.update(topk_score=np.full((n, _abi.TW_K), np.nan), topk_idx=np.full(_abi.TW_K * nt, -1, np.int32),
+                   topk_cnt=np.zeros(n, np.uint8))
+    final = _abi.TwPassOut(_ptr(res["assign"]), _ptr(res["mis_rank"]), _ptr(res["n_cand"]), None, None, None,
+                           _ptr(res["counters"]))
+    top = _abi.TwScoreOut(_ptr(res.get("topk_score")), _ptr(res.get("topk_idx")), _ptr(res.get("topk_cnt")),
+                          None, None)
+    st = batch_struct(hb, lambda name: _ptr(hb.arrays[name]))
+    _check(L.two_find_assignments(C.byref(st), C.c_uint32(seed_select), C.c_int(threads), C.byref(final),
+                                  C.byref(top) if want_topk else None, _ptr(res["n_cand_total"]), _ptr(res["mix"])),
+           "find_assignments")
+    return res

@@ -37,6 +37,7 @@ def case(request, engine):
     prob = g.problem()
     hb = build_batch([prob])
     engine.bind(hb)
+    engine.prepare()
     return g, prob, hb, engine
 
 
@@ -120,6 +121,7 @@ def test_all_goldens_in_one_batch(engine):
     probs = [g.problem() for g in gs]
     hb = build_batch(probs)
     engine.bind(hb)
+    engine.prepare()
     gauss = np.concatenate([g.gauss_table(p).reshape(-1, 3) for g, p in zip(gs, probs)])
     mix = np.concatenate([g.mix_table(p) for g, p in zip(gs, probs)])
     cut = engine.score()["cut"]

@@ -61,6 +61,7 @@ def test_refit_kernel_matches_sklearn(engine, path):
     prob = g.problem()
     hb = build_batch([prob])
     engine.bind(hb)
+    engine.prepare()
     n, E = prob.n_in, prob.E
     assign0 = np.full((E, n), -1, np.int32)
     mis0, idx0 = g.z["mis_rank"][0], g.z["topk_idx"][0]

@@ -161,3 +161,81 @@ def batch_struct(hb: HostBatch, ptr):
                  "ep_pred_mask", "term_src", "in_start", "in_end", "out_start", "out_end"):
         setattr(s, name, ptr(name))
     return s
+
+
+@dataclass
+class ServiceBlock:
+    """S services with identical shape (n_in, E, DAG): the vectorised form used by the synthetic
+    generators.  Arrays are [S, n]; out lists are per ep in topological order."""
+    in_start: np.ndarray
+    in_end: np.ndarray
+    out_start: List[np.ndarray]
+    out_end: List[np.ndarray]
+    preds: List[List[int]]
+    truth: np.ndarray = None            # [E, S, n] index of the true child in each ep list
+    name: str = ""
+
+    def problem(self, s) -> Problem:
+        return Problem(in_start=self.in_start[s], in_end=self.in_end[s],
+                       out_start=[o[s] for o in self.out_start], out_end=[o[s] for o in self.out_end],
+                       preds=self.preds, name=f"{self.name}[{s}]")
+
+
+def build_batch_from_blocks(blocks: Sequence[ServiceBlock]) -> HostBatch:
+    """Same arrays as build_batch([...problems of every block...]) without per-problem Python work."""
+    prob_in, prob_ep, prob_tuple = [0], [0], [0]
+    ep_out, ep_term, ep_pred, term_src = [0], [0], [], []
+    ins, ine, outs, oute = [], [], [], []
+    for blk in blocks:
+        S, n = blk.in_start.shape
+        E = len(blk.out_start)
+        tmpl = Problem(in_start=blk.in_start[0], in_end=blk.in_end[0], out_start=[o[0] for o in blk.out_start],
+                       out_end=[o[0] for o in blk.out_end], preds=blk.preds, name=blk.name)
+        tmpl.validate()
+        terms = tmpl.terms()
+        per_ep_terms = [[src for (ee, src) in terms if ee == e] for e in range(E)]
+        masks = [sum(1 << b for b in blk.preds[e]) for e in range(E)]
+        base_in, base_ep, base_tuple = prob_in[-1], prob_ep[-1], prob_tuple[-1]
+        prob_in.extend(base_in + n * np.arange(1, S + 1))
+        prob_ep.extend(base_ep + E * np.arange(1, S + 1))
+        prob_tuple.extend(base_tuple + n * E * np.arange(1, S + 1))
+        base_out, base_term = ep_out[-1], ep_term[-1]
+        ep_out.extend(base_out + n * np.arange(1, S * E + 1))
+        cum = np.cumsum([len(t) for t in per_ep_terms])
+        nt = int(cum[-1])
+        ep_term.extend((base_term + nt * np.arange(S)[:, None] + cum[None, :]).reshape(-1))
+        ep_pred.extend(masks * S)
+        term_src.extend([src for t in per_ep_terms for src in t] * S)
+        ins.append(blk.in_start.reshape(-1))
+        ine.append(blk.in_end.reshape(-1))
+        # per problem: ep 0 list, ep 1 list, ...  -> stack [S, E, n]
+        outs.append(np.stack(blk.out_start, axis=1).reshape(-1))
+        oute.append(np.stack(blk.out_end, axis=1).reshape(-1))
+    arrays = dict(
+        prob_in_off=np.asarray(prob_in, np.int64), prob_ep_off=np.asarray(prob_ep, np.int32),
+        prob_tuple_off=np.asarray(prob_tuple, np.int64), ep_out_off=np.asarray(ep_out, np.int64),
+        ep_term_off=np.asarray(ep_term, np.int32), ep_pred_mask=np.asarray(ep_pred, np.uint32),
+        term_src=np.asarray(term_src, np.int8),
+        in_start=np.ascontiguousarray(np.concatenate(ins), np.int64),
+        in_end=np.ascontiguousarray(np.concatenate(ine), np.int64),
+        out_start=np.ascontiguousarray(np.concatenate(outs), np.int64),
+        out_end=np.ascontiguousarray(np.concatenate(oute), np.int64))
+    P = len(prob_in) - 1
+    n_in = np.diff(arrays["prob_in_off"])
+    n_batches = (n_in + _abi.TW_PARAM_BATCH - 1) // _abi.TW_PARAM_BATCH
+    n_terms = np.diff(arrays["ep_term_off"].astype(np.int64)[arrays["prob_ep_off"]])
+    arrays["prob_gauss_off"] = np.concatenate([[0], np.cumsum(n_batches * n_terms)]).astype(np.int64)
+    term_prob = np.repeat(np.arange(P), n_terms)
+    arrays["term_sample_off"] = np.concatenate([[0], np.cumsum(n_in[term_prob])]).astype(np.int64)
+    hb = HostBatch(problems=_ProblemCount(P), arrays=arrays)
+    return hb
+
+
+class _ProblemCount:
+    """len()-only stand-in for the problem list of a block-built batch."""
+
+    def __init__(self, n):
+        self.n = n
+
+    def __len__(self):
+        return self.n

@@ -4,6 +4,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <random>
 #include <string>
 #include <vector>
@@ -36,8 +37,9 @@ struct tw_engine {
   std::vector<int64_t> prob_in_off;
   std::vector<int32_t> prob_ep_off;
   int max_seg = 0;
-  // device scratch (owned)
-  std::vector<void*> owned;
+  // device scratch (owned, grow-only: re-binding a batch of similar size allocates nothing)
+  struct Slot { void* p = nullptr; size_t bytes = 0; };
+  std::map<void*, Slot> slots;
   int32_t* prev_idx = nullptr;
   int32_t* narrow_tiles = nullptr;   // [2*n]: prob, start
   int32_t* wide_tiles = nullptr;     // [3*n]: prob, start, narrow index
@@ -65,19 +67,29 @@ struct tw_engine {
   uint32_t gmm_seed = 0;
   bool gmm_seed_valid = false;
 
+  bool gmm_stream100_valid = false;
   void release() {
-    for (void* p : owned) cudaFree(p);
-    owned.clear();
+    for (auto& kv : slots) cudaFree(kv.second.p);
+    slots.clear();
     bound = false;
-    gmm_max_n = nullptr;
     gmm_seed_valid = false;
+    gmm_stream100_valid = false;
   }
   template <class T>
   cudaError_t alloc(T** out, size_t count) {
-    void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(T));
-    if (e == cudaSuccess) { owned.push_back(p); *out = (T*)p; }
-    return e;
+    size_t need = (count ? count : 1) * sizeof(T);
+    Slot& sl = slots[(void*)out];
+    if (sl.bytes < need) {
+      if (sl.p) cudaFree(sl.p);
+      sl.p = nullptr;
+      sl.bytes = 0;
+      size_t cap = need + need / 8;
+      cudaError_t e = cudaMalloc(&sl.p, cap);
+      if (e != cudaSuccess) return e;
+      sl.bytes = cap;
+    }
+    *out = (T*)sl.p;
+    return cudaSuccess;
   }
 };
 
@@ -160,7 +172,7 @@ int tw_engine_bind(tw_engine* eng, const tw_batch* dev, const tw_batch* h, void*
   int rc = tw_batch_validate_host(h);
   if (rc) return rc;
   CU(cudaSetDevice(eng->device));
-  eng->release();
+  eng->bound = false;
   eng->dev = *dev;
   const int P = h->n_problems;
   eng->prob_in_off.assign(h->prob_in_off, h->prob_in_off + P + 1);
@@ -227,12 +239,18 @@ int tw_engine_bind(tw_engine* eng, const tw_batch* dev, const tw_batch* h, void*
   CU(cudaMemsetAsync(eng->err_flag, 0, sizeof(int), s));
   CU(cudaStreamSynchronize(s));   // staging vectors go out of scope
 
-  // ---- batch-constant pre-kernels
-  CU(launch_prev_index(eng->dev, eng->prev_idx, s));
   if (eng->max_seg > 16384) return fail(TW_ERR_RANGE_LIMIT, "bind: a service has more than 16384 spans per list (sort limit)");
+  eng->bound = true;
+  return TW_OK;
+}
+
+int tw_prepare(tw_engine* eng, void* stream_) {
+  if (!eng || !eng->bound) return fail(TW_ERR_INVALID, "tw_prepare: no batch bound");
+  cudaStream_t s = (cudaStream_t)stream_;
+  CU(cudaSetDevice(eng->device));
+  CU(launch_prev_index(eng->dev, eng->prev_idx, s));
   CU(launch_sort_ends(eng->dev, eng->in_end_sorted, eng->out_end_sorted, eng->max_seg, eng->err_flag, s));
   eng->launches += 2;
-  eng->bound = true;
   return TW_OK;
 }
 
@@ -317,18 +335,18 @@ static void numpy_random_samples(uint32_t seed, int count, std::vector<double>& 
 
 static int gmm_prepare(tw_engine* eng, uint32_t seed_select, cudaStream_t s) {
   const int nt = eng->dev.n_term_total;
-  if (!eng->gmm_max_n) {
-    CU(eng->alloc(&eng->gmm_max_n, (size_t)nt));
-    CU(eng->alloc(&eng->gmm_mean_var, (size_t)nt * 2));
-    CU(eng->alloc(&eng->gmm_skip, (size_t)nt));
-    CU(eng->alloc(&eng->gmm_bic, (size_t)nt * TW_GMM_MAX_COMP));
-    CU(eng->alloc(&eng->gmm_stream, (size_t)tw_engine::kStreamLen));
-    CU(eng->alloc(&eng->gmm_stream100, 16));
+  CU(eng->alloc(&eng->gmm_max_n, (size_t)nt));
+  CU(eng->alloc(&eng->gmm_mean_var, (size_t)nt * 2));
+  CU(eng->alloc(&eng->gmm_skip, (size_t)nt));
+  CU(eng->alloc(&eng->gmm_bic, (size_t)nt * TW_GMM_MAX_COMP));
+  CU(eng->alloc(&eng->gmm_stream, (size_t)tw_engine::kStreamLen));
+  CU(eng->alloc(&eng->gmm_stream100, 16));
+  if (!eng->gmm_stream100_valid) {
     std::vector<double> s100;
     numpy_random_samples(100u, 16, s100);
     CU(cudaMemcpyAsync(eng->gmm_stream100, s100.data(), 16 * sizeof(double), cudaMemcpyHostToDevice, s));
     CU(cudaStreamSynchronize(s));
-    eng->gmm_seed_valid = false;
+    eng->gmm_stream100_valid = true;
   }
   if (!eng->gmm_seed_valid || eng->gmm_seed != seed_select) {
     std::vector<double> st;

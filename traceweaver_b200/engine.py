@@ -94,6 +94,10 @@ class Engine:
         self.n_tuple = int(hb.prob_tuple_off[-1])
         return self
 
+    def prepare(self):
+        """tw_prepare: prev-index scan + end-time sort (part of the path, once per batch)."""
+        _lib.check(self.lib.tw_prepare(self.h, self.stream), "tw_prepare")
+
     def status(self):
         _lib.check(self.lib.tw_engine_status(self.h, self.stream), "tw_engine_status")
 

@@ -26,6 +26,12 @@ def solve_batch(eng: Engine, hb, seed_select=10, truth_assign=None, term_order=N
     params0 -> windows -> stitch (pass 0) -> delays -> refit -> score (final top-K) -> stitch
     (pass 1).  Returns device tensors; one host sync at the end (engine status)."""
     eng.bind(hb, device_arrays=device_arrays, pinned=pinned)
+    return solve_bound(eng, seed_select, truth_assign, term_order)
+
+
+def solve_bound(eng: Engine, seed_select=10, truth_assign=None, term_order=None):
+    """Both passes over the batch currently bound to `eng` (inputs resident in HBM)."""
+    eng.prepare()                                 # prev-index scan, sorted end times
     p0 = eng.params_pass0()                       # ComputeEpPairDistParams3, every 100-span batch
     sc = eng.score()                              # CreateWindows2: perfect-cut flags
     r0 = eng.stitch(p0, sc["cut"])                # iteration 0

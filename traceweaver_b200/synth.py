@@ -1,0 +1,97 @@
+"""Synthetic span streams of the shapes BASELINE.json names: many independent
+services, each a stream of incoming requests that fan out to E outgoing endpoints along a fixed
+invocation DAG, int64 microsecond timestamps from 1.6e15, n_out == n_in (no skips), ground truth
+kept.  Delay/duration laws are log-normal, calibrated on the reference's hotel_reservation traces
+(tests/golden fixtures: Poisson arrivals with 33 ms mean inter-arrival at load 100, ~250 us
+dispatch gaps, 4-18 ms downstream calls).  Generation is host-side numpy and is NOT part of any
+timed region."""
+import numpy as np
+
+from .batch import ServiceBlock
+
+T0 = 1_655_760_000_000_000     # us; same epoch range as the Jaeger startTime values
+
+# shape -> (preds, per-ep (gap median us, gap sigma, dur median us, dur sigma), tail median, mode)
+SHAPES = {
+    # hotel frontend: search -> reservation -> profile, plus the transitive search -> profile edge
+    "hotel_frontend": dict(preds=[[], [0], [0, 1]], eps=[(270, 0.6, 15400, 0.45), (195, 0.7, 7300, 1.2),
+                                                           (210, 0.6, 4150, 0.55)], tail=(165, 0.7), chain=True),
+    # hotel search: geo -> rate
+    "hotel_search": dict(preds=[[], [0]], eps=[(267, 0.6, 3700, 0.5), (165, 0.8, 7300, 0.6)], tail=(68, 0.8),
+                         chain=True),
+    # media nginx: four parallel endpoints, no DAG edges
+    "media_nginx": dict(preds=[[], [], [], []], eps=[(250, 0.6, 2500, 0.6), (300, 0.6, 3000, 0.6),
+                                                     (350, 0.6, 1500, 0.6), (400, 0.6, 4000, 0.6)],
+                        tail=(200, 0.7), chain=False),
+    "single": dict(preds=[[]], eps=[(250, 0.6, 5000, 0.6)], tail=(150, 0.7), chain=True),
+}
+INTERARRIVAL_US_AT_LOAD_100 = 33_300.0
+
+
+def _lognormal(rng, median, sigma, shape, floor=1):
+    v = rng.lognormal(np.log(median), sigma, size=shape)
+    return np.maximum(np.rint(v), floor).astype(np.int64)
+
+
+def make_block(shape: str, n_services: int, n_in: int = 1000, load: float = 100.0, seed: int = 10) -> ServiceBlock:
+    spec = SHAPES[shape]
+    rng = np.random.default_rng(seed)
+    S, n = n_services, n_in
+    E = len(spec["eps"])
+    ia = np.maximum(np.rint(rng.exponential(INTERARRIVAL_US_AT_LOAD_100 * 100.0 / load, size=(S, n))), 1).astype(np.int64)
+    in_start = T0 + np.cumsum(ia, axis=1)
+    t = in_start.copy()
+    latest = in_start.copy()
+    starts, ends = [], []
+    for e, (gm, gs, dm, ds) in enumerate(spec["eps"]):
+        base = t if spec["chain"] else in_start
+        s = base + _lognormal(rng, gm, gs, (S, n))
+        en = s + _lognormal(rng, dm, ds, (S, n))
+        starts.append(s)
+        ends.append(en)
+        t = en
+        latest = np.maximum(latest, en)
+    in_end = latest + _lognormal(rng, spec["tail"][0], spec["tail"][1], (S, n))
+    out_start, out_end, truth = [], [], np.empty((E, S, n), np.int32)
+    rows = np.arange(S)[:, None]
+    for e in range(E):
+        order = np.argsort(starts[e], axis=1, kind="stable")
+        s_sorted = np.take_along_axis(starts[e], order, axis=1)
+        e_sorted = np.take_along_axis(ends[e], order, axis=1)
+        tie_rows = np.flatnonzero((np.diff(s_sorted, axis=1) == 0).any(axis=1))
+        for r in tie_rows:        # (start, end) order where starts tie (executor.py:1111-1112)
+            o2 = np.lexsort((ends[e][r], starts[e][r]))
+            order[r] = o2
+            s_sorted[r] = starts[e][r][o2]
+            e_sorted[r] = ends[e][r][o2]
+        inv = np.empty_like(order)
+        inv[rows, order] = np.arange(n)[None, :]
+        out_start.append(np.ascontiguousarray(s_sorted))
+        out_end.append(np.ascontiguousarray(e_sorted))
+        truth[e] = inv
+    return ServiceBlock(in_start=np.ascontiguousarray(in_start), in_end=np.ascontiguousarray(in_end),
+                        out_start=out_start, out_end=out_end, preds=spec["preds"], truth=truth,
+                        name=f"{shape}@load{load:g}")
+
+
+def hotel_stream(n_services: int, n_in: int = 1000, loads=(25, 50, 75, 100, 125, 150), seed: int = 10):
+    """hotel_reservation-shaped stream: alternating `frontend` (E=3) and `search` (E=2) services over
+    the six load levels of the reference's dataset directories."""
+    blocks = []
+    per = max(1, n_services // (2 * len(loads)))
+    k = 0
+    for li, load in enumerate(loads):
+        for shape in ("hotel_frontend", "hotel_search"):
+            cnt = per if (li, shape) != (len(loads) - 1, "hotel_search") else max(1, n_services - per * (2 * len(loads) - 1))
+            blocks.append(make_block(shape, cnt, n_in, load, seed + k))
+            k += 1
+    return blocks
+
+
+def span_count(blocks):
+    return int(sum(b.in_start.size * (1 + len(b.out_start)) for b in blocks))
+
+
+def truth_assign(blocks):
+    """Ground-truth assignment array in the engine's layout (assign[tuple_off[p] + e*n + i])."""
+    return np.concatenate([np.transpose(b.truth, (1, 0, 2)).reshape(-1) for b in blocks]).astype(np.int32)
