@@ -28,9 +28,12 @@ SHAPES = {
 INTERARRIVAL_US_AT_LOAD_100 = 33_300.0
 
 
+MAX_CALL_US = 150_000   # downstream calls time out: the reference's hotel traces top out near 150 ms
+
+
 def _lognormal(rng, median, sigma, shape, floor=1):
     v = rng.lognormal(np.log(median), sigma, size=shape)
-    return np.maximum(np.rint(v), floor).astype(np.int64)
+    return np.clip(np.rint(v), floor, MAX_CALL_US).astype(np.int64)
 
 
 def make_block(shape: str, n_services: int, n_in: int = 1000, load: float = 100.0, seed: int = 10) -> ServiceBlock:
