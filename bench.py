@@ -138,7 +138,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
 
     # ---- this rank's shard of the stream (synthetic, seeded; generation is not timed)
-    blocks = synth.hotel_stream(args.services, args.n_in, seed=args.seed + 1000 * rank)
+    from traceweaver_b200 import shard
+    blocks = synth.hotel_stream(args.services, args.n_in, seed=shard.shard_seed(args.seed, rank))
     hb = build_batch_from_blocks(blocks)
     n_spans = synth.span_count(blocks)
     truth = torch.from_numpy(synth.truth_assign(blocks)).to(dev)
