@@ -14,6 +14,40 @@
 
 using namespace tw;
 
+// Slots available for term tables (shared memory in the kernels).  Tests set it small to force the
+// lazy per-leaf path and large to force the table path.
+static int g_table_cap = 4096;
+extern "C" void twe_set_table_cap(int cap) { g_table_cap = cap; }
+
+// one in-span through the table path: fill -> evaluate every slot -> DFS with look-ups
+template <class Taken>
+static long long enumerate_with_tables(const ProbView& v, const ParamView& pv, int64_t in_s, int64_t in_e,
+                                       const OutWin* w, const int* lo, const int* r, int table_size, Taken taken,
+                                       TopK& tk, uint32_t* mark, int W, int* overflow) {
+  std::vector<double> tbl((size_t)table_size + 1);
+  std::vector<uint8_t> sid((size_t)table_size + 1);
+  int o_last[TW_MAX_E], lo_abs[TW_MAX_E];
+  term_table_last_offsets(v, r, o_last);
+  for (int e = 0; e < v.E; ++e) lo_abs[e] = w[e].base + lo[e];
+  term_table_fill(v, in_s, in_e, w, lo, r, o_last, 0, taken, tbl.data(), sid.data());
+  for (int s = 0; s < table_size; ++s)              // the dense, lane-parallel pass of the kernels
+    if (sid[s] != TW_SLOT_INVALID) tbl[s] = term_logpdf(pv, sid[s] & 63, tbl[s]);
+  long long leaves = 0;
+  enumerate(v, in_s, in_e, w, lo,
+            [&](int e, int o) { return sid[o_last[e] + (o - lo_abs[e])] == TW_SLOT_INVALID; },
+            [&](const int* c, const int64_t*, const int64_t* ce) {
+              ++leaves;
+              if (mark)
+                for (int e = 0; e < v.E; ++e) {
+                  int bit = c[e] - lo_abs[e];
+                  if (bit >= 32 * W) { *overflow = 1; continue; }
+                  mark[e * W + (bit >> 5)] |= 1u << (bit & 31);
+                }
+              topk_offer(v, tk, table_score(v, r, lo_abs, tbl.data(), c, ce), c);
+            });
+  return leaves;
+}
+
 static ParamView param_view(const tw_params* prm, const ProbView& v, int p, int i) {
   ParamView pv;
   pv.mode = prm->mode;
@@ -57,16 +91,24 @@ extern "C" int twe_score_problem(const tw_batch* b, int p, const tw_params* prm,
     ParamView pv;
     if (prm) pv = param_view(prm, v, p, i);
     int64_t in_s = v.is[i], in_e = v.ie[i];
-    enumerate(v, in_s, in_e, w, lo, [](int, int) { return false; },
-              [&](const int* c, const int64_t* cs, const int64_t* ce) {
-                ++leaves;
-                for (int e = 0; e < v.E; ++e) {
-                  int bit = c[e] - lo[e];
-                  if (bit >= 32 * W) { *overflow = 1; continue; }
-                  mine[e * W + (bit >> 5)] |= 1u << (bit & 31);
-                }
-                if (prm) topk_offer(v, tk, score_tuple(v, pv, in_s, in_e, cs, ce), c);
-              });
+    int r[TW_MAX_E];
+    for (int e = 0; e < v.E; ++e) r[e] = range_len(w[e], lo[e], in_e);
+    int tsize = term_table_size(v, r);
+    if (prm && tsize <= g_table_cap) {
+      leaves = enumerate_with_tables(v, pv, in_s, in_e, w, lo, r, tsize, [](int, int) { return false; }, tk, mine,
+                                     W, overflow);
+    } else {
+      enumerate(v, in_s, in_e, w, lo, [](int, int) { return false; },
+                [&](const int* c, const int64_t* cs, const int64_t* ce) {
+                  ++leaves;
+                  for (int e = 0; e < v.E; ++e) {
+                    int bit = c[e] - lo[e];
+                    if (bit >= 32 * W) { *overflow = 1; continue; }
+                    mine[e * W + (bit >> 5)] |= 1u << (bit & 31);
+                  }
+                  if (prm) topk_offer(v, tk, score_tuple(v, pv, in_s, in_e, cs, ce), c);
+                });
+    }
     out->n_feasible[v.in_off + i] = (int32_t)leaves;
     if (prm && out->topk_score) {
       out->topk_cnt[v.in_off + i] = (uint8_t)tk.n;
@@ -127,11 +169,20 @@ extern "C" int twe_stitch_problem(const tw_batch* b, int p, const tw_params* prm
       long long leaves = 0;
       ParamView pv = param_view(prm, v, p, i);
       int64_t in_s = v.is[i], in_e = v.ie[i];
-      enumerate(v, in_s, in_e, w, lo, [&](int e, int o) { return taken[e][o] != 0; },
-                [&](const int* c, const int64_t* cs, const int64_t* ce) {
-                  ++leaves;
-                  topk_offer(v, tk, score_tuple(v, pv, in_s, in_e, cs, ce), c);
-                });
+      int r[TW_MAX_E];
+      for (int e = 0; e < v.E; ++e) r[e] = range_len(w[e], lo[e], in_e);
+      int tsize = term_table_size(v, r);
+      auto is_taken = [&](int e, int o) { return taken[e][o] != 0; };
+      if (tsize <= g_table_cap) {
+        int ov = 0;
+        leaves = enumerate_with_tables(v, pv, in_s, in_e, w, lo, r, tsize, is_taken, tk, nullptr, 0, &ov);
+      } else {
+        enumerate(v, in_s, in_e, w, lo, is_taken,
+                  [&](const int* c, const int64_t* cs, const int64_t* ce) {
+                    ++leaves;
+                    topk_offer(v, tk, score_tuple(v, pv, in_s, in_e, cs, ce), c);
+                  });
+      }
       out->n_cand[v.in_off + i] = (int32_t)leaves;
       wb->cnt[l] = tk.n;
       for (int k = 0; k < tk.n; ++k) {

@@ -21,6 +21,11 @@ def lib():
     return _LIB
 
 
+def set_table_cap(cap):
+    """Term-table slots available per in-span (0 forces the per-leaf path)."""
+    lib().twe_set_table_cap(int(cap))
+
+
 class EmulBatch(OracleBatch):
     """Same interface as OracleBatch, but running the engine's own per-thread code."""
 

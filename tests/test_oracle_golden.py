@@ -8,6 +8,7 @@ import pytest
 
 from golden_util import Golden, golden_files
 from oracle import tw_oracle
+import emul_backend
 from emul_backend import EmulBatch
 from traceweaver_b200 import _abi
 from traceweaver_b200.batch import build_batch
@@ -21,7 +22,25 @@ def test_goldens_present():
     assert len(FILES) >= 10
 
 
-BACKENDS = {"oracle": tw_oracle.OracleBatch, "emul": EmulBatch}
+class EmulLazy(EmulBatch):
+    """Same device functions with the term tables disabled (per-leaf evaluation path)."""
+
+    def score(self, *a, **k):
+        emul_backend.set_table_cap(0)
+        try:
+            return super().score(*a, **k)
+        finally:
+            emul_backend.set_table_cap(4096)
+
+    def stitch(self, *a, **k):
+        emul_backend.set_table_cap(0)
+        try:
+            return super().stitch(*a, **k)
+        finally:
+            emul_backend.set_table_cap(4096)
+
+
+BACKENDS = {"oracle": tw_oracle.OracleBatch, "emul": EmulBatch, "emul-lazy": EmulLazy}
 
 
 @pytest.fixture(scope="module", params=[(f, b) for f in FILES for b in BACKENDS],

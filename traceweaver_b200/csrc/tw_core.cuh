@@ -250,6 +250,119 @@ TW_HD void enumerate(const ProbView& v, int64_t in_s, int64_t in_e, const OutWin
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Term tables.  The score of a tuple is a sum of terms that each depend on ONE candidate (root,
+// last) or on a PAIR of candidates (primary edge), so all distinct term values of an in-span fit
+// a small table: for ep e with r_e candidates in range, r_e values per root/last term and
+// r_b * r_e per edge term b->e.  The kernels (1) lay the tables of a tile / window out
+// back to back in shared memory, (2) write (term id, dt) into every slot, (3) evaluate all slots
+// with every lane busy — this is where the FP64 exp/log/div work of GetEpPairCost (V1:117-139)
+// goes — and (4) run the DFS with look-ups only.  Values and summation order are unchanged, so
+// scores are bit-identical to evaluating each leaf from scratch.
+//
+// Slot id byte: bits 0-5 = problem-local term index (< TW_MAX_TERMS), bits 6-7 = parameter batch
+// relative to the tile's / window's first batch (pass 0 has one Gaussian table per 100 in-spans);
+// 0xFF = slot no feasible tuple can use (candidate outside the in-span, taken, or pair out of order).
+// ---------------------------------------------------------------------------------------------
+#define TW_SLOT_INVALID 0xFF
+
+// spans of the window from `lo` on whose start is <= in_e (the in-span's candidate range of one ep)
+TW_HD int range_len(const OutWin& w, int lo, int64_t in_e) {
+  int x = lo;
+  while (x < w.n && w.s[x] <= in_e) ++x;
+  return x - lo;
+}
+
+TW_HD int term_table_size(const ProbView& v, const int* r) {
+  int tot = 0;
+  for (int e = 0; e < v.E; ++e)
+    for (int t = v.term_lo[e]; t < v.term_lo[e + 1]; ++t) {
+      int src = v.term_src[t];
+      tot += src >= 0 ? r[src] * r[e] : r[e];
+    }
+  return tot;
+}
+
+// offset of the LAST term's sub-table of every ep (its slot ids double as candidate validity)
+TW_HD void term_table_last_offsets(const ProbView& v, const int* r, int* o_last) {
+  int o = 0;
+  for (int e = 0; e < v.E; ++e)
+    for (int t = v.term_lo[e]; t < v.term_lo[e + 1]; ++t) {
+      int src = v.term_src[t];
+      if (src == TW_TERM_LAST) o_last[e] = o;
+      o += src >= 0 ? r[src] * r[e] : r[e];
+    }
+}
+
+// Writes dt (as double) and the slot id of every entry.  `brel` = parameter batch of this in-span
+// relative to the tile / window base.  Taken is `bool(int ep, int orig_index)`.
+template <class Taken>
+TW_HD void term_table_fill(const ProbView& v, int64_t in_s, int64_t in_e, const OutWin* w, const int* lo,
+                           const int* r, const int* o_last, int brel, Taken taken, double* tbl,
+                           uint8_t* sid) {
+  const uint8_t bb = (uint8_t)(brel << 6);
+  // candidate validity first (LAST sub-tables): contained and not taken (V3:328-333)
+  for (int e = 0; e < v.E; ++e) {
+    const int t_last = v.term_lo[e + 1] - 1;
+    for (int x = 0; x < r[e]; ++x) {
+      int64_t en = w[e].e[lo[e] + x];
+      bool ok = en <= in_e && !taken(e, w[e].base + lo[e] + x);
+      tbl[o_last[e] + x] = (double)(in_e - en);                                    // V1:354-355
+      sid[o_last[e] + x] = ok ? (uint8_t)(t_last | bb) : (uint8_t)TW_SLOT_INVALID;
+    }
+  }
+  int o = 0;
+  for (int e = 0; e < v.E; ++e)
+    for (int t = v.term_lo[e]; t < v.term_lo[e + 1]; ++t) {
+      int src = v.term_src[t];
+      if (src >= 0) {                                                              // V1:345
+        for (int xb = 0; xb < r[src]; ++xb) {
+          bool vb = sid[o_last[src] + xb] != TW_SLOT_INVALID;
+          int64_t eb = w[src].e[lo[src] + xb];
+          for (int xe = 0; xe < r[e]; ++xe) {
+            int64_t s = w[e].s[lo[e] + xe];
+            bool ok = vb && eb <= s && sid[o_last[e] + xe] != TW_SLOT_INVALID;
+            tbl[o] = (double)(s - eb);
+            sid[o] = ok ? (uint8_t)(t | bb) : (uint8_t)TW_SLOT_INVALID;
+            ++o;
+          }
+        }
+      } else if (src == TW_TERM_ROOT) {                                            // V1:349-350
+        for (int xe = 0; xe < r[e]; ++xe) {
+          tbl[o] = (double)(w[e].s[lo[e] + xe] - in_s);
+          sid[o] = sid[o_last[e] + xe] != TW_SLOT_INVALID ? (uint8_t)(t | bb) : (uint8_t)TW_SLOT_INVALID;
+          ++o;
+        }
+      } else {
+        o += r[e];
+      }
+    }
+}
+
+// score of a tuple from evaluated tables: same terms, same order as score_tuple()
+TW_HD double table_score(const ProbView& v, const int* r, const int* lo_abs, const double* tbl, const int* c,
+                         const int64_t* ce) {
+  int last = 0;
+  for (int e = 1; e < v.E; ++e)
+    if (ce[e] > ce[last]) last = e;
+  double cost = 0.0;
+  int o = 0;
+  for (int e = 0; e < v.E; ++e) {
+    const int xe = c[e] - lo_abs[e];
+    for (int t = v.term_lo[e]; t < v.term_lo[e + 1]; ++t) {
+      int src = v.term_src[t];
+      if (src >= 0) {
+        cost = dadd(cost, tbl[o + (c[src] - lo_abs[src]) * r[e] + xe]);
+        o += r[src] * r[e];
+      } else {
+        if (src == TW_TERM_ROOT || e == last) cost = dadd(cost, tbl[o + xe]);
+        o += r[e];
+      }
+    }
+  }
+  return cost;
+}
+
 // first index in [0, n) of a sorted array with a[idx] >= key
 TW_HD int lower_bound(const int64_t* a, int n, int64_t key) {
   int lo = 0, hi = n;

@@ -11,7 +11,9 @@ namespace tw {
 constexpr int kScoreThreads = 128;               // one in-span per thread
 constexpr int kScoreTile = kScoreThreads - 1;    // in-spans per CTA; the last thread enumerates
                                                  // the tile's carry-in "prev" in-span (PerfectCut)
-constexpr int kStageSpans = 2048;                // out spans staged in shared memory per tile
+constexpr int kStageSpans = 1536;                // out spans staged in shared memory per tile
+constexpr int kTblCap = 3072;                    // term-table slots per CTA round (tw_core.cuh)
+constexpr int kWarpTblCap = 640;                 // term-table slots per stitch warp
 constexpr int kNarrowW = 2;                      // bitmap words per (in-span, ep): 64 candidates
 constexpr int kWideW = 64;                       // overflow kernel: 2048 candidates per ep
 constexpr int kWideThreads = 32;                 // (31 in-spans + carry-in per CTA)

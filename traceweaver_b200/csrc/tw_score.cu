@@ -72,6 +72,10 @@ struct ScoreSmem {
   int64_t st_s[kStageSpans];
   int64_t st_e[kStageSpans];
   double prm[TW_MAX_TERMS * TW_MIX_REC];     // mixture table, or up to three Gaussian batch tables
+  double tbl[kTblCap];                        // term tables of the in-spans of the current round
+  uint8_t sid[kTblCap];                       // slot ids (term | batch << 6), TW_SLOT_INVALID
+  int scan[T / 32];
+  int tbl_total;
   uint32_t used[T][TW_MAX_E][W];
   int lo_abs[T][TW_MAX_E];
   int64_t red[T / 32];
@@ -183,10 +187,12 @@ k_score(tw_batch b, tw_params prm, int has_params, tw_score_out out, TileList ti
     for (int wq = 0; wq < W; ++wq) sm.used[tid][e][wq] = 0u;
   __syncthreads();
 
-  // ---- per-thread enumeration
+  // ---- per-thread candidate ranges
+  OutWin w[TW_MAX_E];
+  int lo[TW_MAX_E], r[TW_MAX_E];
+  int tsize = 0;
+  const bool do_score = has_params && worker;
   if (worker || helper) {
-    OutWin w[TW_MAX_E];
-    int lo[TW_MAX_E];
     for (int e = 0; e < E; ++e) {
       if (helper && sm.staged) {   // carry-in span lies before the staged slice: use global arrays
         w[e].s = v.os[e]; w[e].e = v.oe[e]; w[e].base = 0; w[e].n = v.n_out[e];
@@ -195,40 +201,122 @@ k_score(tw_batch b, tw_params prm, int has_params, tw_score_out out, TileList ti
       }
       lo[e] = lower_bound(w[e].s, w[e].n, in_s);
       sm.lo_abs[tid][e] = w[e].base + lo[e];
+      r[e] = do_score ? range_len(w[e], lo[e], in_e) : 0;
     }
-    ParamView pv;
-    pv.mode = prm.mode;
-    pv.gauss = sm.prm + (i / TW_PARAM_BATCH - batch0) * v.n_terms * TW_GAUSS_REC;
-    pv.mix = sm.prm;
-    TopK tk;
-    tk.n = 0;
+    if (do_score) tsize = term_table_size(v, r);
+  }
+  uint32_t (*mine)[W] = sm.used[tid];
+  const int* lo_abs = sm.lo_abs[tid];
+  auto mark = [&](const int* c, bool& ovf) {
+    for (int e = 0; e < E; ++e) {
+      int bit = c[e] - lo_abs[e];
+      if (bit >= 32 * W) ovf = true;
+      else mine[e][bit >> 5] |= 1u << (bit & 31);
+    }
+  };
+  auto write_out = [&](const TopK& tk, int leaves) {
+    int64_t gi = v.in_off + i;
+    out.n_feasible[gi] = leaves;
+    if (do_score && out.topk_score) {
+      out.topk_cnt[gi] = (uint8_t)tk.n;
+      int32_t* ix = out.topk_idx + TW_K * (v.tuple_off + (int64_t)i * E);
+      for (int k = 0; k < TW_K; ++k) {
+        out.topk_score[gi * TW_K + k] = k < tk.n ? tk.score[k] : __longlong_as_double(0x7ff8000000000000LL);
+        for (int e = 0; e < E; ++e) ix[k * E + e] = k < tk.n ? tk.idx[k][e] : -1;
+      }
+    }
+  };
+  // windows-only launches and the carry-in helper only mark (no likelihoods)
+  if ((worker || helper) && !do_score) {
     int leaves = 0;
     bool ovf = false;
-    const bool do_score = has_params && worker;
-    uint32_t (*mine)[W] = sm.used[tid];
-    const int* lo_abs = sm.lo_abs[tid];
     enumerate(v, in_s, in_e, w, lo, [](int, int) { return false; },
-              [&](const int* c, const int64_t* cs, const int64_t* ce) {
+              [&](const int* c, const int64_t*, const int64_t*) {
                 if (leaves < 0x7fffffff) ++leaves;
-                for (int e = 0; e < E; ++e) {
-                  int bit = c[e] - lo_abs[e];
-                  if (bit >= 32 * W) ovf = true;
-                  else mine[e][bit >> 5] |= 1u << (bit & 31);
-                }
-                if (do_score) topk_offer(v, tk, score_tuple(v, pv, in_s, in_e, cs, ce), c);
+                mark(c, ovf);
               });
     if (ovf) sm.overflow = 1;
-    if (worker) {
-      int64_t gi = v.in_off + i;
-      out.n_feasible[gi] = leaves;
-      if (do_score && out.topk_score) {
-        out.topk_cnt[gi] = (uint8_t)tk.n;
-        int32_t* ix = out.topk_idx + TW_K * (v.tuple_off + (int64_t)i * E);
-        for (int k = 0; k < TW_K; ++k) {
-          out.topk_score[gi * TW_K + k] = k < tk.n ? tk.score[k] : __longlong_as_double(0x7ff8000000000000LL);
-          for (int e = 0; e < E; ++e) ix[k * E + e] = k < tk.n ? tk.idx[k][e] : -1;
+    if (worker) { TopK none; none.n = 0; write_out(none, leaves); }
+  }
+  // ---- scoring: term tables in shared memory, evaluated by the whole CTA (see tw_core.cuh)
+  if (has_params) {
+    bool pending = do_score;
+    const int lane = tid & 31, wid = tid >> 5;
+    while (true) {
+      // exclusive prefix of the pending threads' table sizes
+      int my = pending ? tsize : 0, incl = my;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      if (lane == 31) sm.scan[wid] = incl;
+      if (tid == 0) sm.tbl_total = 0;
+      __syncthreads();
+      int offset = incl - my;
+      for (int q = 0; q < wid; ++q) offset += sm.scan[q];
+      const bool lazy = pending && offset == 0 && tsize > kTblCap;     // does not fit at all
+      const bool in_round = pending && !lazy && offset + tsize <= kTblCap;
+      int o_last[TW_MAX_E];
+      const int brel = i / TW_PARAM_BATCH - batch0;
+      if (in_round) {
+        term_table_last_offsets(v, r, o_last);
+        term_table_fill(v, in_s, in_e, w, lo, r, o_last, brel, [](int, int) { return false; }, sm.tbl + offset,
+                        sm.sid + offset);
+        atomicMax(&sm.tbl_total, offset + tsize);
+      }
+      if (lazy) {   // per-leaf evaluation for an in-span whose tables exceed shared memory
+        ParamView pv;
+        pv.mode = prm.mode;
+        pv.gauss = sm.prm + brel * v.n_terms * TW_GAUSS_REC;
+        pv.mix = sm.prm;
+        TopK tk;
+        tk.n = 0;
+        int leaves = 0;
+        bool ovf = false;
+        enumerate(v, in_s, in_e, w, lo, [](int, int) { return false; },
+                  [&](const int* c, const int64_t* cs, const int64_t* ce) {
+                    if (leaves < 0x7fffffff) ++leaves;
+                    mark(c, ovf);
+                    topk_offer(v, tk, score_tuple(v, pv, in_s, in_e, cs, ce), c);
+                  });
+        if (ovf) sm.overflow = 1;
+        write_out(tk, leaves);
+        pending = false;
+      }
+      __syncthreads();
+      // dense pass: every lane evaluates slots (GetEpPairCost, V1:117-139)
+      const int total = sm.tbl_total;
+      for (int s = tid; s < total; s += T) {
+        const uint8_t id = sm.sid[s];
+        if (id != TW_SLOT_INVALID) {
+          ParamView pv;
+          pv.mode = prm.mode;
+          pv.gauss = sm.prm + (id >> 6) * v.n_terms * TW_GAUSS_REC;
+          pv.mix = sm.prm;
+          sm.tbl[s] = term_logpdf(pv, id & 63, sm.tbl[s]);
         }
       }
+      __syncthreads();
+      if (in_round) {
+        const double* tbl = sm.tbl + offset;
+        const uint8_t* sid = sm.sid + offset;
+        TopK tk;
+        tk.n = 0;
+        int leaves = 0;
+        bool ovf = false;
+        enumerate(v, in_s, in_e, w, lo,
+                  [&](int e, int o) { return sid[o_last[e] + (o - lo_abs[e])] == TW_SLOT_INVALID; },
+                  [&](const int* c, const int64_t*, const int64_t* ce) {
+                    if (leaves < 0x7fffffff) ++leaves;
+                    mark(c, ovf);
+                    topk_offer(v, tk, table_score(v, r, lo_abs, tbl, c, ce), c);
+                  });
+        if (ovf) sm.overflow = 1;
+        write_out(tk, leaves);
+        pending = false;
+      }
+      if (!__syncthreads_or(pending)) break;
     }
   }
   __syncthreads();

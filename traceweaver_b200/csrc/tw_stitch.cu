@@ -20,6 +20,8 @@ namespace tw {
 struct StitchWarpSmem {
   ProbView v;
   WindowBuf wb;
+  double tbl[kWarpTblCap];     // term tables of the current window (tw_core.cuh)
+  uint8_t sid[kWarpTblCap];
 };
 
 __global__ void __launch_bounds__(kStitchWarps * 32)
@@ -73,27 +75,25 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_pass
     const int nw = we - ws + 1;
     if (nw > TW_WINDOW_CAP) { rc = TW_ERR_INVALID; break; }
 
-    // ---- per-lane candidate search on the not-taken spans
-    int lo0[TW_MAX_E];
-    if (lane < nw) {
-      const int i = ws + lane;
-      const int64_t in_s = v.is[i], in_e = v.ie[i];
-      int lo[TW_MAX_E];
-      for (int e = 0; e < E; ++e) lo[e] = lower_bound_from(w[e].s, w[e].n, cursor[e], in_s);
-      for (int e = 0; e < E; ++e) lo0[e] = lo[e];
-      ParamView pv;
-      pv.mode = prm.mode;
-      pv.gauss = gauss_base ? gauss_base + (int64_t)(i / TW_PARAM_BATCH) * v.n_terms * TW_GAUSS_REC : nullptr;
-      pv.mix = mix_base;
-      TopK tk;
-      tk.n = 0;
-      int leaves = 0;
-      enumerate(v, in_s, in_e, w, lo,
-                [&](int e, int o) { return (tk_base[e][o >> 5] >> (o & 31)) & 1u; },
-                [&](const int* c, const int64_t* cs, const int64_t* ce) {
-                  if (leaves < 0x7fffffff) ++leaves;
-                  topk_offer(v, tk, score_tuple(v, pv, in_s, in_e, cs, ce), c);
-                });
+    // ---- per-lane candidate ranges on the not-taken spans
+    const bool active = lane < nw;
+    const int i = ws + (active ? lane : 0);
+    const int64_t in_s = v.is[i], in_e = v.ie[i];
+    int lo[TW_MAX_E], r[TW_MAX_E], lo_abs[TW_MAX_E];
+    int tsize = 0;
+    for (int e = 0; e < E; ++e) {
+      lo[e] = lower_bound_from(w[e].s, w[e].n, cursor[e], in_s);
+      lo_abs[e] = lo[e];
+      r[e] = active ? range_len(w[e], lo[e], in_e) : 0;
+    }
+    if (active) tsize = term_table_size(v, r);
+    for (int e = 0; e < E; ++e) cursor[e] = __shfl_sync(0xffffffffu, lo[e], 0);
+    auto is_taken = [&](int e, int o) {   // volatile: bits are set by other lanes with atomics
+      return (reinterpret_cast<volatile const uint32_t*>(tk_base[e])[o >> 5] >> (o & 31)) & 1u;
+    };
+    const int batch0 = ws / TW_PARAM_BATCH;
+    const int brel = i / TW_PARAM_BATCH - batch0;
+    auto publish = [&](const TopK& tk, int leaves) {
       const int64_t gi = v.in_off + i;
       out.n_cand[gi] = leaves;
       wb.cnt[lane] = tk.n;
@@ -109,8 +109,73 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_pass
           for (int e = 0; e < E; ++e) ix[k * E + e] = k < tk.n ? tk.idx[k][e] : -1;
         }
       }
+    };
+    // ---- term tables of the window in the warp's shared memory, evaluated by all 32 lanes
+    bool pending = active;
+    while (true) {
+      int my = pending ? tsize : 0, incl = my;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      const int offset = incl - my;
+      const bool lazy = pending && offset == 0 && tsize > kWarpTblCap;
+      const bool in_round = pending && !lazy && offset + tsize <= kWarpTblCap;
+      int total = in_round ? offset + tsize : 0;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) total = max(total, __shfl_xor_sync(0xffffffffu, total, d));
+      int o_last[TW_MAX_E];
+      if (in_round) {
+        term_table_last_offsets(v, r, o_last);
+        term_table_fill(v, in_s, in_e, w, lo, r, o_last, brel, is_taken, sm.tbl + offset, sm.sid + offset);
+      }
+      if (lazy) {   // tables larger than the warp's slab: evaluate per leaf
+        ParamView pv;
+        pv.mode = prm.mode;
+        pv.gauss = gauss_base ? gauss_base + (int64_t)(i / TW_PARAM_BATCH) * v.n_terms * TW_GAUSS_REC : nullptr;
+        pv.mix = mix_base;
+        TopK tk;
+        tk.n = 0;
+        int leaves = 0;
+        enumerate(v, in_s, in_e, w, lo, is_taken,
+                  [&](const int* c, const int64_t* cs, const int64_t* ce) {
+                    if (leaves < 0x7fffffff) ++leaves;
+                    topk_offer(v, tk, score_tuple(v, pv, in_s, in_e, cs, ce), c);
+                  });
+        publish(tk, leaves);
+        pending = false;
+      }
+      __syncwarp();
+      for (int s = lane; s < total; s += 32) {     // GetEpPairCost for every slot, all lanes busy
+        const uint8_t id = sm.sid[s];
+        if (id != TW_SLOT_INVALID) {
+          ParamView pv;
+          pv.mode = prm.mode;
+          pv.gauss = gauss_base ? gauss_base + (int64_t)(batch0 + (id >> 6)) * v.n_terms * TW_GAUSS_REC : nullptr;
+          pv.mix = mix_base;
+          sm.tbl[s] = term_logpdf(pv, id & 63, sm.tbl[s]);
+        }
+      }
+      __syncwarp();
+      if (in_round) {
+        const double* tbl = sm.tbl + offset;
+        const uint8_t* sid = sm.sid + offset;
+        TopK tk;
+        tk.n = 0;
+        int leaves = 0;
+        enumerate(v, in_s, in_e, w, lo,
+                  [&](int e, int o) { return sid[o_last[e] + (o - lo_abs[e])] == TW_SLOT_INVALID; },
+                  [&](const int* c, const int64_t*, const int64_t* ce) {
+                    if (leaves < 0x7fffffff) ++leaves;
+                    topk_offer(v, tk, table_score(v, r, lo_abs, tbl, c, ce), c);
+                  });
+        publish(tk, leaves);
+        pending = false;
+      }
+      if (!__any_sync(0xffffffffu, pending)) break;
+      __syncwarp();
     }
-    for (int e = 0; e < E; ++e) cursor[e] = __shfl_sync(0xffffffffu, lo0[e], 0);
     __syncwarp();
 
     // ---- stitch the window (V3:1192-1219)
