@@ -187,21 +187,20 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_pass
     __syncwarp();
     if (nodes < 0) { rc = TW_ERR_MWIS_LIMIT; break; }
     if (nodes > max_nodes) max_nodes = nodes;
-    int r = -2;
+    int rank = -2;
     if (lane < nw) {
-      const int i = ws + lane;
-      r = wb.chosen[lane];
-      out.mis_rank[v.in_off + i] = (int8_t)r;
-      if (r >= 0) {
+      rank = wb.chosen[lane];
+      out.mis_rank[v.in_off + i] = (int8_t)rank;
+      if (rank >= 0) {
         for (int e = 0; e < E; ++e) {
-          int o = wb.idx[lane][r][e];
+          int o = wb.idx[lane][rank][e];
           out.assign[v.tuple_off + (int64_t)e * n + i] = o;
           atomicOr(&tk_base[e][o >> 5], 1u << (o & 31));
         }
       }
     }
-    not_best += __popc(__ballot_sync(0xffffffffu, lane < nw && r != 0));
-    unassigned += __popc(__ballot_sync(0xffffffffu, lane < nw && r < 0));
+    not_best += __popc(__ballot_sync(0xffffffffu, lane < nw && rank != 0));
+    unassigned += __popc(__ballot_sync(0xffffffffu, lane < nw && rank < 0));
     __threadfence_block();
     __syncwarp();
     ws = we + 1;
