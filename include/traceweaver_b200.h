@@ -120,6 +120,13 @@ typedef struct tw_score_out {
   uint8_t* topk_cnt;      /* [n_in_total]                                                         */
   int32_t* n_feasible;    /* [n_in_total] number of feasible tuples on the undeleted lists         */
   uint8_t* cut;           /* [n_in_total] 1 iff PerfectCut(i) (v3:1024-1039); cut[first]=0         */
+  /* Optional (all three or none): the set of out spans that appear in SOME feasible tuple of the
+   * in-span (candidates_array, v3:1043-1051), as a 64-bit map per (in-span, ep) anchored at
+   * used_lo.  tw_stitch uses it to prove that no candidate of an in-span has been taken, in which
+   * case the top-K on the undeleted lists IS the with-deletion top-K (v3:1182 == v3:1185).       */
+  int32_t* used_lo;       /* [prob_tuple_off[P]]   used_lo[tuple_off[p] + i*E + e]                 */
+  uint32_t* used_bits;    /* [2 * prob_tuple_off[P]]  two words per (in-span, ep)                  */
+  uint8_t* used_wide;     /* [n_in_total] 1 = the in-span's candidates exceed 64 per ep (no map)   */
 } tw_score_out;
 
 typedef struct tw_engine tw_engine;   /* opaque: bound batch, device scratch, error string       */
@@ -181,9 +188,12 @@ int tw_score_topk(tw_engine* eng, const tw_params* params, const tw_score_out* o
  * The sequential part of one pass: windows from cut flags (v3:1056-1076), per in-span top-K on
  * the not-yet-taken out spans (v3:1182), exact MWIS per window (BuildMISInstance v3:1252-1274 +
  * gurobi_optimods.mwis at v3:1411), assignment + deletion (AddAssignment v1:433-463).
+ * `undeleted` (may be NULL) = output of tw_score_topk run with the SAME params including the used
+ * maps: for every in-span none of whose candidates has been taken by an earlier window the kernel
+ * adopts that top-K list instead of searching again; the result is identical either way.
  */
-int tw_stitch(tw_engine* eng, const tw_params* params, const uint8_t* cut, const tw_pass_out* out,
-              void* stream);
+int tw_stitch(tw_engine* eng, const tw_params* params, const uint8_t* cut, const tw_score_out* undeleted,
+              const tw_pass_out* out, void* stream);
 
 /*
  * Delay samples implied by a pass's assignments, per term (ComputeEpPairDistParams5's

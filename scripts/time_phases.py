@@ -26,13 +26,15 @@ def timed(name, fn, reps=3):
 
 timed("prepare (prev+sort)", eng.prepare)
 p0 = timed("params_pass0", eng.params_pass0)
-sc = timed("score (windows only)", eng.score)
-r0 = timed("stitch pass0 (gauss)", lambda: eng.stitch(p0, sc["cut"]))
+timed("score (windows only)", eng.score)
+sc = timed("score (gauss, topk+used)", lambda: eng.score(p0, want_used=True))
+timed("stitch pass0 slow path", lambda: eng.stitch(p0, sc["cut"]))
+r0 = timed("stitch pass0 fast path", lambda: eng.stitch(p0, sc["cut"], undeleted=sc))
 dc = timed("delays", lambda: eng.delays(r0["assign"]))
 p1 = timed("gmm_refit", lambda: eng.gmm_refit(dc[0], dc[1]))
-top = timed("score (gmm, topk)", lambda: eng.score(p1))
-timed("score (gauss, topk)", lambda: eng.score(p0))
-r1 = timed("stitch pass1 (gmm)", lambda: eng.stitch(p1, sc["cut"]))
+top = timed("score (gmm, topk+used)", lambda: eng.score(p1, want_used=True))
+timed("stitch pass1 slow path", lambda: eng.stitch(p1, sc["cut"]))
+r1 = timed("stitch pass1 fast path", lambda: eng.stitch(p1, sc["cut"], undeleted=top))
 eng.status()
 from traceweaver_b200.predictor import solve_bound
 timed("whole path (resident)", lambda: solve_bound(eng))

@@ -99,6 +99,26 @@ def test_hot_loop_pass(case, pass_id):
         assert c[0, 0] == g.meta["not_best_count"] and c[0, 1] == g.meta["cnt_unassigned"] and c[0, 3] == 0
 
 
+@pytest.mark.parametrize("pass_id", [0, 1])
+def test_hot_loop_fast_path_is_identical(case, pass_id):
+    """tw_stitch with the undeleted top-K lists + candidate maps (fast path: nothing taken => adopt)
+    must give exactly the results of the search on the not-taken spans, and the goldens."""
+    g, prob, hb, eng = case
+    prm = eng.params_from_host(gauss=g.gauss_table(prob)) if pass_id == 0 else eng.params_from_host(mix=g.mix_table(prob))
+    und = eng.score(prm, want_used=True)
+    slow = eng.stitch(prm, und["cut"], want_topk=True)
+    fast = eng.stitch(prm, und["cut"], want_topk=True, undeleted=und)
+    eng.status()
+    n, E = prob.n_in, prob.E
+    for k in ("assign", "mis_rank", "n_cand", "topk_cnt", "topk_idx"):
+        assert np.array_equal(_np(slow[k]), _np(fast[k])), k
+    assert np.array_equal(_np(slow["topk_score"]), _np(fast["topk_score"]), equal_nan=True)
+    assert np.array_equal(_np(fast["counters"])[:, :2], _np(slow["counters"])[:, :2])
+    assert np.array_equal(_np(fast["mis_rank"]), g.z["mis_rank"][pass_id])
+    assert np.array_equal(_np(fast["topk_idx"]).reshape(n, 5, E), g.z["topk_idx"][pass_id])
+    assert _np(und["used_wide"]).max() == 0 or prob.E >= 4
+
+
 def test_delays_match_oracle(case):
     from oracle import tw_oracle
     g, prob, hb, eng = case

@@ -48,7 +48,8 @@ class TwPassOut(C.Structure):
 
 
 class TwScoreOut(C.Structure):
-    _fields_ = [("topk_score", P), ("topk_idx", P), ("topk_cnt", P), ("n_feasible", P), ("cut", P)]
+    _fields_ = [("topk_score", P), ("topk_idx", P), ("topk_cnt", P), ("n_feasible", P), ("cut", P),
+                ("used_lo", P), ("used_bits", P), ("used_wide", P)]
 
 
 class TwError(RuntimeError):

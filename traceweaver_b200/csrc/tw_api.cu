@@ -292,6 +292,8 @@ int tw_score_topk(tw_engine* eng, const tw_params* params, const tw_score_out* o
   if (!out || !out->cut || !out->n_feasible) return fail(TW_ERR_INVALID, "tw_score_topk: cut and n_feasible are required");
   if (params && (!out->topk_score || !out->topk_idx || !out->topk_cnt))
     return fail(TW_ERR_INVALID, "tw_score_topk: params given but topk outputs missing");
+  if ((out->used_lo != nullptr) != (out->used_bits != nullptr) || (out->used_lo != nullptr) != (out->used_wide != nullptr))
+    return fail(TW_ERR_INVALID, "tw_score_topk: used_lo / used_bits / used_wide go together");
   TileList narrow{eng->narrow_tiles, eng->narrow_tiles + eng->n_narrow, eng->n_narrow, kScoreTile};
   TileList wide{eng->wide_tiles, eng->wide_tiles + eng->n_wide, eng->n_wide, kWideThreads - 1};
   CU(launch_score(eng->dev, params, *out, narrow, wide, eng->prev_idx, eng->narrow_overflow, eng->err_flag,
@@ -300,13 +302,22 @@ int tw_score_topk(tw_engine* eng, const tw_params* params, const tw_score_out* o
   return TW_OK;
 }
 
-int tw_stitch(tw_engine* eng, const tw_params* params, const uint8_t* cut, const tw_pass_out* out, void* stream) {
+int tw_stitch(tw_engine* eng, const tw_params* params, const uint8_t* cut, const tw_score_out* undeleted,
+              const tw_pass_out* out, void* stream) {
   int rc = need_bound(eng, "tw_stitch");
   if (rc) return rc;
   if (!params || !cut || !out || !out->assign || !out->mis_rank || !out->n_cand)
     return fail(TW_ERR_INVALID, "tw_stitch: params, cut, assign, mis_rank, n_cand are required");
   if (out->topk_score && (!out->topk_idx || !out->topk_cnt)) return fail(TW_ERR_INVALID, "tw_stitch: partial topk outputs");
-  CU(launch_stitch(eng->dev, *params, cut, *out, eng->taken, eng->taken_words, eng->node_limit, eng->err_flag,
+  tw_score_out spec;
+  memset(&spec, 0, sizeof spec);
+  if (undeleted) {
+    if (!undeleted->topk_score || !undeleted->topk_idx || !undeleted->topk_cnt || !undeleted->n_feasible ||
+        !undeleted->used_lo || !undeleted->used_bits || !undeleted->used_wide)
+      return fail(TW_ERR_INVALID, "tw_stitch: `undeleted` needs top-K, n_feasible and the used maps");
+    spec = *undeleted;
+  }
+  CU(launch_stitch(eng->dev, *params, cut, spec, *out, eng->taken, eng->taken_words, eng->node_limit, eng->err_flag,
                    (cudaStream_t)stream));
   eng->launches += 1;
   return TW_OK;

@@ -36,7 +36,7 @@ cudaError_t launch_score(const tw_batch& b, const tw_params* prm, const tw_score
                          const TileList& narrow, const TileList& wide, const int32_t* prev_idx,
                          uint8_t* narrow_overflow, int* err_flag, cudaStream_t s);
 cudaError_t launch_stitch(const tw_batch& b, const tw_params& prm, const uint8_t* cut,
-                          const tw_pass_out& out, uint32_t* taken_words, size_t taken_n_words,
+                          const tw_score_out& spec, const tw_pass_out& out, uint32_t* taken_words, size_t taken_n_words,
                           long long node_limit, int* err_flag, cudaStream_t s);
 cudaError_t launch_sort_ends(const tw_batch& b, int64_t* in_end_sorted, int64_t* out_end_sorted,
                              int max_seg, int* err_flag, cudaStream_t s);

@@ -334,6 +334,19 @@ k_score(tw_batch b, tw_params prm, int has_params, tw_score_out out, TileList ti
       cut = (uint8_t)(disjoint && v.ie[pi] <= in_e);
     }
     out.cut[v.in_off + i] = cut;
+    if (out.used_lo) {   // candidate maps for tw_stitch's "nothing taken" proof
+      const int64_t base = v.tuple_off + (int64_t)i * E;
+      if (W == kNarrowW) {
+        for (int e = 0; e < E; ++e) {
+          out.used_lo[base + e] = sm.lo_abs[tid][e];
+          out.used_bits[2 * (base + e)] = sm.used[tid][e][0];
+          out.used_bits[2 * (base + e) + 1] = sm.used[tid][e][1];
+        }
+        out.used_wide[v.in_off + i] = 0;
+      } else {
+        out.used_wide[v.in_off + i] = 1;
+      }
+    }
   }
   if (tid == 0 && sm.overflow) {
     if (redo_only) atomicMin(err_flag, (int)TW_ERR_RANGE_LIMIT);

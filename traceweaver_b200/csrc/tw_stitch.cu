@@ -25,7 +25,7 @@ struct StitchWarpSmem {
 };
 
 __global__ void __launch_bounds__(kStitchWarps * 32)
-k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_pass_out out,
+k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_score_out spec, tw_pass_out out,
          uint32_t* __restrict__ taken, long long node_limit, int* __restrict__ err_flag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp_in_block = threadIdx.x >> 5;
@@ -63,8 +63,6 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_pass
 
   WindowCursor wc;
   wc.init();
-  int cursor[TW_MAX_E];
-  for (int e = 0; e < E; ++e) cursor[e] = 0;
   int not_best = 0, unassigned = 0;
   long long max_nodes = 0;
   int ws = 0;
@@ -79,18 +77,37 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_pass
     const bool active = lane < nw;
     const int i = ws + (active ? lane : 0);
     const int64_t in_s = v.is[i], in_e = v.ie[i];
-    int lo[TW_MAX_E], r[TW_MAX_E], lo_abs[TW_MAX_E];
-    int tsize = 0;
-    for (int e = 0; e < E; ++e) {
-      lo[e] = lower_bound_from(w[e].s, w[e].n, cursor[e], in_s);
-      lo_abs[e] = lo[e];
-      r[e] = active ? range_len(w[e], lo[e], in_e) : 0;
-    }
-    if (active) tsize = term_table_size(v, r);
-    for (int e = 0; e < E; ++e) cursor[e] = __shfl_sync(0xffffffffu, lo[e], 0);
     auto is_taken = [&](int e, int o) {   // volatile: bits are set by other lanes with atomics
       return (reinterpret_cast<volatile const uint32_t*>(tk_base[e])[o >> 5] >> (o & 31)) & 1u;
     };
+    // ---- fast path: none of the in-span's candidates (the spans of its feasible tuples on the
+    // undeleted lists) has been taken => the undeleted top-K list IS FindTopKAssignments(out_copy)
+    bool fast = false;
+    if (active && spec.used_lo && !spec.used_wide[v.in_off + i]) {
+      const int64_t base = v.tuple_off + (int64_t)i * E;
+      uint32_t hit = 0;
+      for (int e = 0; e < E; ++e) {
+        const int ulo = spec.used_lo[base + e];
+        const uint32_t u0 = spec.used_bits[2 * (base + e)], u1 = spec.used_bits[2 * (base + e) + 1];
+        if ((u0 | u1) == 0u) continue;
+        const volatile uint32_t* tkw = reinterpret_cast<volatile const uint32_t*>(tk_base[e]) + (ulo >> 5);
+        const int sh = ulo & 31;
+        const uint32_t a = tkw[0], bq = tkw[1], c2 = tkw[2];
+        hit |= __funnelshift_r(a, bq, sh) & u0;
+        hit |= __funnelshift_r(bq, c2, sh) & u1;
+      }
+      fast = hit == 0u;
+    }
+    int lo[TW_MAX_E], r[TW_MAX_E], lo_abs[TW_MAX_E];
+    int tsize = 0;
+    if (active && !fast) {
+      for (int e = 0; e < E; ++e) {
+        lo[e] = lower_bound(w[e].s, w[e].n, in_s);
+        lo_abs[e] = lo[e];
+        r[e] = range_len(w[e], lo[e], in_e);
+      }
+      tsize = term_table_size(v, r);
+    }
     const int batch0 = ws / TW_PARAM_BATCH;
     const int brel = i / TW_PARAM_BATCH - batch0;
     auto publish = [&](const TopK& tk, int leaves) {
@@ -110,8 +127,28 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_pass
         }
       }
     };
-    // ---- term tables of the window in the warp's shared memory, evaluated by all 32 lanes
-    bool pending = active;
+    if (fast) {   // adopt the list computed on the undeleted spans
+      const int64_t gi = v.in_off + i;
+      const int cnt = spec.topk_cnt[gi];
+      out.n_cand[gi] = spec.n_feasible[gi];
+      wb.cnt[lane] = cnt;
+      const int32_t* ix = spec.topk_idx + TW_K * (v.tuple_off + (int64_t)i * E);
+      for (int k = 0; k < cnt; ++k) {
+        wb.score[lane][k] = spec.topk_score[gi * TW_K + k];
+        for (int e = 0; e < E; ++e) wb.idx[lane][k][e] = ix[k * E + e];
+      }
+      if (out.topk_score) {
+        out.topk_cnt[gi] = (uint8_t)cnt;
+        int32_t* ox = out.topk_idx + TW_K * (v.tuple_off + (int64_t)i * E);
+        for (int k = 0; k < TW_K; ++k) {
+          out.topk_score[gi * TW_K + k] = spec.topk_score[gi * TW_K + k];
+          for (int e = 0; e < E; ++e) ox[k * E + e] = ix[k * E + e];
+        }
+      }
+    }
+    // ---- slow path: term tables of the window in the warp's shared memory, evaluated by all lanes
+    bool pending = active && !fast;
+    if (__any_sync(0xffffffffu, pending))
     while (true) {
       int my = pending ? tsize : 0, incl = my;
 #pragma unroll
@@ -179,11 +216,15 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_pass
     __syncwarp();
 
     // ---- stitch the window (V3:1192-1219)
-    if (lane < nw) wb.adj[lane] = window_adjacency(wb, E, nw, lane);
-    __syncwarp();
-    long long nodes = 0;
-    if (lane == 0) nodes = mwis_solve(wb, E, nw, node_limit);
-    nodes = __shfl_sync(0xffffffffu, nodes, 0);
+    long long nodes = 1;
+    if (nw == 1) {   // one in-span: its best candidate if the vertex weight is positive
+      if (lane == 0) wb.chosen[0] = (wb.cnt[0] > 0 && TW_WEIGHT_OFFSET + wb.score[0][0] > 0.0) ? 0 : -1;
+    } else {
+      if (lane < nw) wb.adj[lane] = window_adjacency(wb, E, nw, lane);
+      __syncwarp();
+      if (lane == 0) nodes = mwis_solve(wb, E, nw, node_limit);
+      nodes = __shfl_sync(0xffffffffu, nodes, 0);
+    }
     __syncwarp();
     if (nodes < 0) { rc = TW_ERR_MWIS_LIMIT; break; }
     if (nodes > max_nodes) max_nodes = nodes;
@@ -217,7 +258,7 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_pass
 }
 
 cudaError_t launch_stitch(const tw_batch& b, const tw_params& prm, const uint8_t* cut,
-                          const tw_pass_out& out, uint32_t* taken_words, size_t taken_n_words,
+                          const tw_score_out& spec, const tw_pass_out& out, uint32_t* taken_words, size_t taken_n_words,
                           long long node_limit, int* err_flag, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(taken_words, 0, taken_n_words * sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
@@ -229,7 +270,7 @@ cudaError_t launch_stitch(const tw_batch& b, const tw_params& prm, const uint8_t
     attr_done = true;
   }
   int blocks = (b.n_problems + kStitchWarps - 1) / kStitchWarps;
-  k_stitch<<<blocks, kStitchWarps * 32, smem, s>>>(b, prm, cut, out, taken_words, node_limit, err_flag);
+  k_stitch<<<blocks, kStitchWarps * 32, smem, s>>>(b, prm, cut, spec, out, taken_words, node_limit, err_flag);
   return cudaGetLastError();
 }
 

@@ -119,25 +119,37 @@ class Engine:
         t = _to_device(np.asarray(gauss, np.float64).reshape(-1, _abi.TW_GAUSS_REC), self.device)
         return Params(_abi.TW_PARAMS_GAUSS_BATCHED, t, self.d["prob_gauss_off"])
 
-    def score(self, params: Params = None, out=None):
+    def score(self, params: Params = None, out=None, want_used=False):
+        """tw_score_topk.  want_used: also emit the candidate maps tw_stitch's fast path needs."""
         dev = self.device
         n, nt = self.n_in, self.n_tuple
         if out is None:
             out = {}
+        if want_used:
+            out.setdefault("used_lo", torch.empty(nt, dtype=torch.int32, device=dev))
+            out.setdefault("used_bits", torch.empty(2 * nt, dtype=torch.int32, device=dev))
+            out.setdefault("used_wide", torch.empty(n, dtype=torch.uint8, device=dev))
         out.setdefault("n_feasible", torch.empty(n, dtype=torch.int32, device=dev))
         out.setdefault("cut", torch.empty(n, dtype=torch.uint8, device=dev))
         if params is not None:
             out.setdefault("topk_score", torch.empty((n, _abi.TW_K), dtype=torch.float64, device=dev))
             out.setdefault("topk_idx", torch.empty(_abi.TW_K * nt, dtype=torch.int32, device=dev))
             out.setdefault("topk_cnt", torch.empty(n, dtype=torch.uint8, device=dev))
-        s = _abi.TwScoreOut(_p(out.get("topk_score")), _p(out.get("topk_idx")), _p(out.get("topk_cnt")),
-                            _p(out["n_feasible"]), _p(out["cut"]))
+        s = self._score_struct(out)
         ps = params.struct() if params is not None else None
         _lib.check(self.lib.tw_score_topk(self.h, C.byref(ps) if ps is not None else None, C.byref(s),
                                           self.stream), "tw_score_topk")
         return out
 
-    def stitch(self, params: Params, cut, want_topk=False, out=None):
+    @staticmethod
+    def _score_struct(out):
+        return _abi.TwScoreOut(_p(out.get("topk_score")), _p(out.get("topk_idx")), _p(out.get("topk_cnt")),
+                               _p(out.get("n_feasible")), _p(out.get("cut")), _p(out.get("used_lo")),
+                               _p(out.get("used_bits")), _p(out.get("used_wide")))
+
+    def stitch(self, params: Params, cut, want_topk=False, out=None, undeleted=None):
+        """tw_stitch.  undeleted: result of score(params, want_used=True) with the SAME params; lets
+        the kernel adopt those top-K lists wherever no candidate has been taken (identical result)."""
         dev = self.device
         n, nt = self.n_in, self.n_tuple
         if out is None:
@@ -153,7 +165,9 @@ class Engine:
         s = _abi.TwPassOut(_p(out["assign"]), _p(out["mis_rank"]), _p(out["n_cand"]), _p(out.get("topk_score")),
                            _p(out.get("topk_idx")), _p(out.get("topk_cnt")), _p(out["counters"]))
         ps = params.struct()
-        _lib.check(self.lib.tw_stitch(self.h, C.byref(ps), _p(cut), C.byref(s), self.stream), "tw_stitch")
+        und = self._score_struct(undeleted) if undeleted is not None else None
+        _lib.check(self.lib.tw_stitch(self.h, C.byref(ps), _p(cut), C.byref(und) if und is not None else None,
+                                      C.byref(s), self.stream), "tw_stitch")
         return out
 
     def gmm_refit(self, delays, counts, seed_select=10, prob_base_skip=None, term_order=None, want_selected=False):

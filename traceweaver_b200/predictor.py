@@ -33,8 +33,9 @@ def solve_bound(eng: Engine, seed_select=10, truth_assign=None, term_order=None)
     """Both passes over the batch currently bound to `eng` (inputs resident in HBM)."""
     eng.prepare()                                 # prev-index scan, sorted end times
     p0 = eng.params_pass0()                       # ComputeEpPairDistParams3, every 100-span batch
-    sc = eng.score()                              # CreateWindows2: perfect-cut flags
-    r0 = eng.stitch(p0, sc["cut"])                # iteration 0
+    # CreateWindows2 (perfect-cut flags) + FindTopKAssignments on the undeleted lists, pass-0 params
+    sc = eng.score(p0, want_used=True)
+    r0 = eng.stitch(p0, sc["cut"], undeleted=sc)  # iteration 0
     delays, counts = eng.delays(r0["assign"])     # ComputeEpPairDistParams5: durations
     base = None
     if truth_assign is not None:
@@ -43,8 +44,9 @@ def solve_bound(eng: Engine, seed_select=10, truth_assign=None, term_order=None)
         dt, ct = eng.delays(truth_assign)
         base = eng.gmm_stream_draws(dt, ct)
     p1 = eng.gmm_refit(delays, counts, seed_select=seed_select, prob_base_skip=base, term_order=term_order)
-    top = eng.score(p1)                           # top_k_2 of the last iteration -> all_topk_assignments
-    r1 = eng.stitch(p1, sc["cut"])                # iteration 1
+    # top_k_2 of the last iteration -> all_topk_assignments; candidate maps are parameter independent
+    top = eng.score(p1, out=dict(used_lo=sc["used_lo"], used_bits=sc["used_bits"], used_wide=sc["used_wide"]))
+    r1 = eng.stitch(p1, sc["cut"], undeleted=top)  # iteration 1
     n_cand = r0["n_cand"] + r1["n_cand"]          # per_span_candidates accumulates over iterations
     eng.status()
     return dict(assign=r1["assign"], mis_rank=r1["mis_rank"], counters=r1["counters"], n_cand=n_cand,
