@@ -263,10 +263,16 @@ __device__ __forceinline__ double estep(const Fit& f, int k, double x, double* a
 #pragma unroll
   for (int c = 0; c < KC; ++c) {
     if (c < k) {
-      if (a[c] == amax) m += 1.0;
-      else s += exp(a[c] - amax);
+      if (a[c] == amax) { m += 1.0; a[c] = 1.0; }
+      else { a[c] = exp(a[c] - amax); s += a[c]; }
     }
   }
+  // a[] now holds exp(a_c - amax): responsibilities are a_c / (m + s) = exp(a_c - logsumexp),
+  // so the E-step costs one exp per component instead of two
+  const double inv = 1.0 / (m + s);
+#pragma unroll
+  for (int c = 0; c < KC; ++c)
+    if (c < k) a[c] *= inv;
   if (m > 1.0) return log1p(s / m) + log(m) + amax;
   return log1p(s) + amax;
 }
@@ -329,7 +335,7 @@ __device__ bool warp_fit(const double* __restrict__ x, int n, int k, double mean
 #pragma unroll
       for (int c = 0; c < KC; ++c)
         if (c < k) {
-          double r = exp(a[c] - l);
+          double r = a[c];
           S0[c] += r; S1[c] += r * xs;
           if (!FULL) S2[c] += r * (xs * xs);
         }
@@ -346,11 +352,11 @@ __device__ bool warp_fit(const double* __restrict__ x, int n, int k, double mean
       for (int c = 0; c < KC; ++c) S2[c] = 0.0;
       for (int i = lane; i < n; i += 32) {
         double xi = x[i], a[KC];
-        double l = estep<FULL>(f, k, xi, a);
+        (void)estep<FULL>(f, k, xi, a);
         double xs = xi - shift;
 #pragma unroll
         for (int c = 0; c < KC; ++c)
-          if (c < k) { double d = xs - mup[c]; S2[c] += (exp(a[c] - l) * d) * d; }
+          if (c < k) { double d = xs - mup[c]; S2[c] += (a[c] * d) * d; }
       }
 #pragma unroll
       for (int c = 0; c < KC; ++c) S2[c] = wsum(S2[c]);
@@ -456,7 +462,7 @@ __global__ void k_gmm_draws(int n_problems, const int32_t* __restrict__ prob_ep_
   prob_draws[p] = pos;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 5)
 k_gmm_bic(int n_terms, const int64_t* __restrict__ term_sample_off, const double* __restrict__ delays,
           const int32_t* __restrict__ counts, const int32_t* __restrict__ max_n,
           const double* __restrict__ mean_var, const uint32_t* __restrict__ rng_skip,
@@ -484,7 +490,7 @@ k_gmm_bic(int n_terms, const int64_t* __restrict__ term_sample_off, const double
   if (lane == 0) bic_out[(size_t)t * KC + (k - 1)] = bic;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 5)
 k_gmm_final(int n_terms, const int64_t* __restrict__ term_sample_off, const double* __restrict__ delays,
             const int32_t* __restrict__ counts, const int32_t* __restrict__ max_n,
             const double* __restrict__ mean_var, const double* __restrict__ bic,
