@@ -18,6 +18,10 @@ using namespace tw;
 // lazy per-leaf path and large to force the table path.
 static int g_table_cap = 4096;
 extern "C" void twe_set_table_cap(int cap) { g_table_cap = cap; }
+// In-spans with more than g_light_combos candidate combinations go through the lane-parallel path
+// (32 lanes stride over the combos, partial top-K lists are merged); -1 disables it.
+static long long g_light_combos = -1;
+extern "C" void twe_set_light_combos(long long c) { g_light_combos = c; }
 
 // one in-span through the table path: fill -> evaluate every slot -> DFS with look-ups
 template <class Taken>
@@ -33,6 +37,41 @@ static long long enumerate_with_tables(const ProbView& v, const ParamView& pv, i
   for (int s = 0; s < table_size; ++s)              // the dense, lane-parallel pass of the kernels
     if (sid[s] != TW_SLOT_INVALID) tbl[s] = term_logpdf(pv, sid[s] & 63, tbl[s]);
   long long leaves = 0;
+  const long long P = combo_count(v, r);
+  if (g_light_combos >= 0 && P > g_light_combos && P < (1LL << 40)) {
+    const int L = 32;
+    std::vector<TopK> part(L);
+    for (int lane = 0; lane < L; ++lane) {
+      part[lane].n = 0;
+      enumerate_combos(v, w, lo, r, o_last, sid.data(), lane, L, P,
+                       [&](const int* c, const int64_t* ce, long long) {
+                         ++leaves;
+                         if (mark)
+                           for (int e = 0; e < v.E; ++e) {
+                             int bit = c[e] - lo_abs[e];
+                             if (bit >= 32 * W) { *overflow = 1; continue; }
+                             mark[e * W + (bit >> 5)] |= 1u << (bit & 31);
+                           }
+                         topk_offer(v, part[lane], table_score(v, r, lo_abs, tbl.data(), c, ce), c);
+                       });
+    }
+    int head[32] = {0};
+    for (int k = 0; k < TW_K; ++k) {      // K rounds of "best head over the lanes"
+      int best = -1;
+      for (int lane = 0; lane < L; ++lane) {
+        if (head[lane] >= part[lane].n) continue;
+        if (best < 0 || cand_ahead(v, part[lane].score[head[lane]], part[lane].idx[head[lane]],
+                                   part[best].score[head[best]], part[best].idx[head[best]]))
+          best = lane;
+      }
+      if (best < 0) break;
+      tk.score[tk.n] = part[best].score[head[best]];
+      for (int e = 0; e < v.E; ++e) tk.idx[tk.n][e] = part[best].idx[head[best]][e];
+      ++tk.n;
+      ++head[best];
+    }
+    return leaves;
+  }
   enumerate(v, in_s, in_e, w, lo,
             [&](int e, int o) { return sid[o_last[e] + (o - lo_abs[e])] == TW_SLOT_INVALID; },
             [&](const int* c, const int64_t*, const int64_t* ce) {

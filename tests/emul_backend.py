@@ -26,6 +26,11 @@ def set_table_cap(cap):
     lib().twe_set_table_cap(int(cap))
 
 
+def set_light_combos(c):
+    """In-spans with more candidate combinations than this use the lane-parallel path (-1: never)."""
+    lib().twe_set_light_combos(C.c_longlong(int(c)))
+
+
 class EmulBatch(OracleBatch):
     """Same interface as OracleBatch, but running the engine's own per-thread code."""
 

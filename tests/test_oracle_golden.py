@@ -40,7 +40,25 @@ class EmulLazy(EmulBatch):
             emul_backend.set_table_cap(4096)
 
 
-BACKENDS = {"oracle": tw_oracle.OracleBatch, "emul": EmulBatch, "emul-lazy": EmulLazy}
+class EmulCombos(EmulBatch):
+    """Every in-span through the lane-parallel combination path + partial top-K merge."""
+
+    def score(self, *a, **k):
+        emul_backend.set_light_combos(0)
+        try:
+            return super().score(*a, **k)
+        finally:
+            emul_backend.set_light_combos(-1)
+
+    def stitch(self, *a, **k):
+        emul_backend.set_light_combos(0)
+        try:
+            return super().stitch(*a, **k)
+        finally:
+            emul_backend.set_light_combos(-1)
+
+
+BACKENDS = {"oracle": tw_oracle.OracleBatch, "emul": EmulBatch, "emul-lazy": EmulLazy, "emul-combos": EmulCombos}
 
 
 @pytest.fixture(scope="module", params=[(f, b) for f in FILES for b in BACKENDS],

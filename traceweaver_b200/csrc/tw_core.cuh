@@ -363,6 +363,59 @@ TW_HD double table_score(const ProbView& v, const int* r, const int* lo_abs, con
   return cost;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Lane-parallel form of the enumeration for in-spans with many candidate tuples.  The candidate
+// product space prod_e r_e is indexed x0-major ("combo"), so ascending combo order IS the DFS leaf
+// order of enumerate().  Lanes take combos first, first+step, ...; a combo is a feasible tuple iff
+// every candidate slot is valid (term_table_fill) and every DAG edge is ordered (V3:335-347).
+// Leaf(c, ce, combo).
+// ---------------------------------------------------------------------------------------------
+TW_HD long long combo_count(const ProbView& v, const int* r) {
+  long long p = 1;
+  for (int e = 0; e < v.E; ++e) {
+    p *= r[e];
+    if (p > (1LL << 40)) return 1LL << 40;
+  }
+  return p;
+}
+
+template <class Leaf>
+TW_HD void enumerate_combos(const ProbView& v, const OutWin* w, const int* lo, const int* r, const int* o_last,
+                            const uint8_t* sid, long long first, long long step, long long P, Leaf leaf) {
+  for (long long combo = first; combo < P; combo += step) {
+    int x[TW_MAX_E], c[TW_MAX_E];
+    int64_t cs[TW_MAX_E], ce[TW_MAX_E];
+    long long idx = combo;
+    bool ok = true;
+    for (int e = v.E - 1; e >= 0; --e) {
+      x[e] = (int)(idx % r[e]);
+      idx /= r[e];
+      if (sid[o_last[e] + x[e]] == TW_SLOT_INVALID) ok = false;
+    }
+    if (!ok) continue;
+    for (int e = 0; e < v.E && ok; ++e) {
+      cs[e] = w[e].s[lo[e] + x[e]];
+      ce[e] = w[e].e[lo[e] + x[e]];
+      c[e] = w[e].base + lo[e] + x[e];
+      uint32_t pm = v.pred[e];
+      for (int b = 0; b < e; ++b)
+        if ((pm >> b & 1u) && ce[b] > cs[e]) { ok = false; break; }
+    }
+    if (ok) leaf(c, ce, combo);
+  }
+}
+
+// total order used when partial top-K lists are merged: the reference's (score, stack) order and,
+// where that order calls two tuples equal, the earlier DFS leaf first (what a single sequential
+// enumeration with topk_offer produces)
+TW_HD bool cand_ahead(const ProbView& v, double sa, const int* ca, double sb, const int* cb) {
+  if (cand_less(v, sb, cb, sa, ca)) return true;
+  if (cand_less(v, sa, ca, sb, cb)) return false;
+  for (int e = 0; e < v.E; ++e)
+    if (ca[e] != cb[e]) return ca[e] < cb[e];
+  return false;
+}
+
 // first index in [0, n) of a sorted array with a[idx] >= key
 TW_HD int lower_bound(const int64_t* a, int n, int64_t key) {
   int lo = 0, hi = n;

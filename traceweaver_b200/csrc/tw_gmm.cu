@@ -154,6 +154,7 @@ __device__ void kmeans_label_centers(const double* __restrict__ x, int n, int k,
 #pragma unroll
     for (int j = 0; j < KC; ++j) { sx[j] = 0.0; cnt[j] = 0.0; }
     bool changed = !have_prev;
+#pragma unroll 2
     for (int i = lane; i < n; i += 32) {
       double xi = x[i] - mean;
       int lab = nearest(cen, k, xi);
@@ -327,6 +328,7 @@ __device__ bool warp_fit(const double* __restrict__ x, int n, int k, double mean
     double prev = lower, part = 0.0;
 #pragma unroll
     for (int c = 0; c < KC; ++c) { S0[c] = 0.0; S1[c] = 0.0; S2[c] = 0.0; }
+#pragma unroll 2
     for (int i = lane; i < n; i += 32) {
       double xi = x[i], a[KC];
       double l = estep<FULL>(f, k, xi, a);
@@ -350,6 +352,7 @@ __device__ bool warp_fit(const double* __restrict__ x, int n, int k, double mean
     if (FULL) {   // responsibilities under the OLD parameters, deviations from the NEW means
 #pragma unroll
       for (int c = 0; c < KC; ++c) S2[c] = 0.0;
+#pragma unroll 2
       for (int i = lane; i < n; i += 32) {
         double xi = x[i], a[KC];
         (void)estep<FULL>(f, k, xi, a);
@@ -366,6 +369,7 @@ __device__ bool warp_fit(const double* __restrict__ x, int n, int k, double mean
   }
   if (want_score) {
     double part = 0.0;
+#pragma unroll 2
     for (int i = lane; i < n; i += 32) { double a[KC]; part += estep<FULL>(f, k, x[i], a); }
     *score = wsum(part) / (double)n;
   }
@@ -462,7 +466,7 @@ __global__ void k_gmm_draws(int n_problems, const int32_t* __restrict__ prob_ep_
   prob_draws[p] = pos;
 }
 
-__global__ void __launch_bounds__(128, 5)
+__global__ void __launch_bounds__(128, 4)
 k_gmm_bic(int n_terms, const int64_t* __restrict__ term_sample_off, const double* __restrict__ delays,
           const int32_t* __restrict__ counts, const int32_t* __restrict__ max_n,
           const double* __restrict__ mean_var, const uint32_t* __restrict__ rng_skip,
@@ -490,7 +494,7 @@ k_gmm_bic(int n_terms, const int64_t* __restrict__ term_sample_off, const double
   if (lane == 0) bic_out[(size_t)t * KC + (k - 1)] = bic;
 }
 
-__global__ void __launch_bounds__(128, 5)
+__global__ void __launch_bounds__(128, 4)
 k_gmm_final(int n_terms, const int64_t* __restrict__ term_sample_off, const double* __restrict__ delays,
             const int32_t* __restrict__ counts, const int32_t* __restrict__ max_n,
             const double* __restrict__ mean_var, const double* __restrict__ bic,
