@@ -154,7 +154,6 @@ __device__ void kmeans_label_centers(const double* __restrict__ x, int n, int k,
 #pragma unroll
     for (int j = 0; j < KC; ++j) { sx[j] = 0.0; cnt[j] = 0.0; }
     bool changed = !have_prev;
-#pragma unroll 2
     for (int i = lane; i < n; i += 32) {
       double xi = x[i] - mean;
       int lab = nearest(cen, k, xi);
@@ -265,9 +264,16 @@ __device__ __forceinline__ double estep(const Fit& f, int k, double x, double* a
   for (int c = 0; c < KC; ++c) {
     if (c < k) {
       if (a[c] == amax) { m += 1.0; a[c] = 1.0; }
-      else { a[c] = exp(a[c] - amax); s += a[c]; }
+      else {
+        // exp(d) < 2^-57 for d < -40: adding it to m >= 1 cannot change a double, and its effect
+        // on log1p(s) is below 1e-17 absolute — skip the (software, ~30 instruction) FP64 exp
+        const double d = a[c] - amax;
+        a[c] = d < -40.0 ? 0.0 : exp(d);
+        s += a[c];
+      }
     }
   }
+  if (s == 0.0 && m == 1.0) return amax;   // one component dominates: logsumexp == its log-prob
   // a[] now holds exp(a_c - amax): responsibilities are a_c / (m + s) = exp(a_c - logsumexp),
   // so the E-step costs one exp per component instead of two
   const double inv = 1.0 / (m + s);
@@ -328,7 +334,6 @@ __device__ bool warp_fit(const double* __restrict__ x, int n, int k, double mean
     double prev = lower, part = 0.0;
 #pragma unroll
     for (int c = 0; c < KC; ++c) { S0[c] = 0.0; S1[c] = 0.0; S2[c] = 0.0; }
-#pragma unroll 2
     for (int i = lane; i < n; i += 32) {
       double xi = x[i], a[KC];
       double l = estep<FULL>(f, k, xi, a);
@@ -352,7 +357,6 @@ __device__ bool warp_fit(const double* __restrict__ x, int n, int k, double mean
     if (FULL) {   // responsibilities under the OLD parameters, deviations from the NEW means
 #pragma unroll
       for (int c = 0; c < KC; ++c) S2[c] = 0.0;
-#pragma unroll 2
       for (int i = lane; i < n; i += 32) {
         double xi = x[i], a[KC];
         (void)estep<FULL>(f, k, xi, a);
@@ -369,7 +373,6 @@ __device__ bool warp_fit(const double* __restrict__ x, int n, int k, double mean
   }
   if (want_score) {
     double part = 0.0;
-#pragma unroll 2
     for (int i = lane; i < n; i += 32) { double a[KC]; part += estep<FULL>(f, k, x[i], a); }
     *score = wsum(part) / (double)n;
   }
@@ -466,7 +469,7 @@ __global__ void k_gmm_draws(int n_problems, const int32_t* __restrict__ prob_ep_
   prob_draws[p] = pos;
 }
 
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, 5)
 k_gmm_bic(int n_terms, const int64_t* __restrict__ term_sample_off, const double* __restrict__ delays,
           const int32_t* __restrict__ counts, const int32_t* __restrict__ max_n,
           const double* __restrict__ mean_var, const uint32_t* __restrict__ rng_skip,
@@ -494,7 +497,7 @@ k_gmm_bic(int n_terms, const int64_t* __restrict__ term_sample_off, const double
   if (lane == 0) bic_out[(size_t)t * KC + (k - 1)] = bic;
 }
 
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, 5)
 k_gmm_final(int n_terms, const int64_t* __restrict__ term_sample_off, const double* __restrict__ delays,
             const int32_t* __restrict__ counts, const int32_t* __restrict__ max_n,
             const double* __restrict__ mean_var, const double* __restrict__ bic,

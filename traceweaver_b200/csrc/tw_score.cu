@@ -76,10 +76,6 @@ struct ScoreSmem {
   uint8_t sid[kTblCap];                       // slot ids (term | batch << 6), TW_SLOT_INVALID
   int scan[T / 32];
   int tbl_total;
-  int rr[T][TW_MAX_E];                        // candidate range lengths of queued (heavy) in-spans
-  int toff[T];                                // their table offsets
-  int heavy_tid[T];
-  int n_heavy;
   uint32_t used[T][TW_MAX_E][W];
   int lo_abs[T][TW_MAX_E];
   int64_t red[T / 32];
@@ -255,7 +251,7 @@ k_score(tw_batch b, tw_params prm, int has_params, tw_score_out out, TileList ti
         if (lane >= d) incl += o;
       }
       if (lane == 31) sm.scan[wid] = incl;
-      if (tid == 0) { sm.tbl_total = 0; sm.n_heavy = 0; }
+      if (tid == 0) sm.tbl_total = 0;
       __syncthreads();
       int offset = incl - my;
       for (int q = 0; q < wid; ++q) offset += sm.scan[q];
@@ -302,16 +298,7 @@ k_score(tw_batch b, tw_params prm, int has_params, tw_score_out out, TileList ti
         }
       }
       __syncthreads();
-      // in-spans with few candidate combinations: the owner thread walks the tuples; the others are
-      // queued and each is enumerated by a whole warp (lanes stride over the combinations)
-      const long long P = in_round ? combo_count(v, r) : 0;
-      const bool heavy = in_round && P > kLightCombos && P < (1LL << 31);
-      if (heavy) {
-        for (int e = 0; e < E; ++e) sm.rr[tid][e] = r[e];
-        sm.toff[tid] = offset;
-        sm.heavy_tid[atomicAdd(&sm.n_heavy, 1)] = tid;
-        pending = false;
-      } else if (in_round) {
+      if (in_round) {
         const double* tbl = sm.tbl + offset;
         const uint8_t* sid = sm.sid + offset;
         TopK tk;
@@ -328,78 +315,6 @@ k_score(tw_batch b, tw_params prm, int has_params, tw_score_out out, TileList ti
         if (ovf) sm.overflow = 1;
         write_out(tk, leaves);
         pending = false;
-      }
-      __syncthreads();
-      for (int h = wid; h < sm.n_heavy; h += T / 32) {
-        const int o = sm.heavy_tid[h];
-        const int oi = i0 + o;
-        int rr[TW_MAX_E], lo_rel[TW_MAX_E], lo_ab[TW_MAX_E], ol[TW_MAX_E];
-        OutWin ww[TW_MAX_E];
-        for (int e = 0; e < E; ++e) {
-          rr[e] = sm.rr[o][e];
-          lo_ab[e] = sm.lo_abs[o][e];
-          ww[e] = sm.win[e];
-          lo_rel[e] = lo_ab[e] - ww[e].base;
-        }
-        term_table_last_offsets(v, rr, ol);
-        const double* tbl = sm.tbl + sm.toff[o];
-        const uint8_t* sid = sm.sid + sm.toff[o];
-        const long long PP = combo_count(v, rr);
-        TopK part;
-        part.n = 0;
-        int leaves = 0;
-        bool ovf = false;
-        enumerate_combos(v, ww, lo_rel, rr, ol, sid, lane, 32, PP,
-                         [&](const int* c, const int64_t* ce, long long) {
-                           ++leaves;
-                           for (int e = 0; e < E; ++e) {
-                             int bit = c[e] - lo_ab[e];
-                             if (bit >= 32 * W) ovf = true;
-                             else atomicOr(&sm.used[o][e][bit >> 5], 1u << (bit & 31));
-                           }
-                           topk_offer(v, part, table_score(v, rr, lo_ab, tbl, c, ce), c);
-                         });
-        if (ovf) sm.overflow = 1;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) leaves += __shfl_xor_sync(0xffffffffu, leaves, d);
-        // merge the lanes' partial lists: K rounds of "best head over the warp" (cand_ahead order)
-        TopK res;
-        res.n = 0;
-        int head = 0;
-        for (int k = 0; k < TW_K; ++k) {
-          int bh = head < part.n, bl = lane;
-          double bs = bh ? part.score[head] : 0.0;
-          int bc[TW_MAX_E];
-          for (int e = 0; e < E; ++e) bc[e] = bh ? part.idx[head][e] : 0;
-#pragma unroll
-          for (int d = 16; d > 0; d >>= 1) {
-            int oh = __shfl_xor_sync(0xffffffffu, bh, d), oln = __shfl_xor_sync(0xffffffffu, bl, d);
-            double os = __shfl_xor_sync(0xffffffffu, bs, d);
-            int oc[TW_MAX_E];
-            for (int e = 0; e < E; ++e) oc[e] = __shfl_xor_sync(0xffffffffu, bc[e], d);
-            if (oh && (!bh || cand_ahead(v, os, oc, bs, bc))) {
-              bh = oh; bl = oln; bs = os;
-              for (int e = 0; e < E; ++e) bc[e] = oc[e];
-            }
-          }
-          if (!bh) break;
-          res.score[res.n] = bs;
-          for (int e = 0; e < E; ++e) res.idx[res.n][e] = bc[e];
-          ++res.n;
-          if (bl == lane) ++head;
-        }
-        if (lane == 0) {
-          const int64_t gi = v.in_off + oi;
-          out.n_feasible[gi] = leaves;
-          if (out.topk_score) {
-            out.topk_cnt[gi] = (uint8_t)res.n;
-            int32_t* ix = out.topk_idx + TW_K * (v.tuple_off + (int64_t)oi * E);
-            for (int k = 0; k < TW_K; ++k) {
-              out.topk_score[gi * TW_K + k] = k < res.n ? res.score[k] : __longlong_as_double(0x7ff8000000000000LL);
-              for (int e = 0; e < E; ++e) ix[k * E + e] = k < res.n ? res.idx[k][e] : -1;
-            }
-          }
-        }
       }
       if (!__syncthreads_or(pending)) break;
     }
