@@ -44,7 +44,7 @@ __device__ __forceinline__ int trials_for_k(int k) { return k < 3 ? 2 : 3; }
 __device__ __forceinline__ int draws_for_k(int k) { return 1 + (k - 1) * trials_for_k(k); }
 
 // _euclidean_distances(squared=True): -2 c x + c^2 + x^2, clipped at 0
-__device__ __noinline__ double sq_dist(double c, double c2, double x, double x2) {
+__device__ __forceinline__ double sq_dist(double c, double c2, double x, double x2) {
   double d = dadd(dadd(dmul(-2.0, dmul(c, x)), c2), x2);
   return d > 0.0 ? d : 0.0;
 }
@@ -53,7 +53,7 @@ struct Fit {
   double mu[KC], pc[KC], logpc[KC], logw[KC];
 };
 
-__device__ __noinline__ int nearest(const double* cen, int k, double x) {
+__device__ __forceinline__ int nearest(const double* cen, int k, double x) {
   int lab = 0;
   double best = dadd(dmul(cen[0], cen[0]), dmul(-2.0, dmul(x, cen[0])));
 #pragma unroll
@@ -67,7 +67,7 @@ __device__ __noinline__ int nearest(const double* cen, int k, double x) {
 
 // KMeans(n_clusters=k, n_init=1).fit(X): returns the centres (on centred data) that define the
 // final labels_.  draws[] = this fit's random_sample() values.
-__device__ __noinline__ void kmeans_label_centers(const double* __restrict__ x, int n, int k, double mean, double tol,
+__device__ void kmeans_label_centers(const double* __restrict__ x, int n, int k, double mean, double tol,
                                      const double* __restrict__ draws, double* cen_out) {
   const int lane = threadIdx.x & 31;
   double cen[KC];
@@ -219,7 +219,7 @@ __device__ __noinline__ void kmeans_label_centers(const double* __restrict__ x, 
 //   'full': S2 = sum r (x' - mu')^2 from a second sweep (_estimate_gaussian_covariances_full),
 //           so a component of identical samples gets cov = reg_covar exactly, as in the library.
 template <bool FULL>
-__device__ __noinline__ bool params_from_stats(Fit& f, int k, int n, const double* nk, const double* mup,
+__device__ __forceinline__ bool params_from_stats(Fit& f, int k, int n, const double* nk, const double* mup,
                                                   const double* S2, double shift, bool init) {
   double tot = 0.0;
   bool ok = true;
@@ -243,7 +243,7 @@ __device__ __noinline__ bool params_from_stats(Fit& f, int k, int n, const doubl
 // weighted log-probabilities of one sample (sklearn _estimate_log_gaussian_prob + log weights)
 // and their logsumexp
 template <bool FULL>
-__device__ __noinline__ double estep(const Fit& f, int k, double x, double* a) {
+__device__ __forceinline__ double estep(const Fit& f, int k, double x, double* a) {
   double amax = -INFINITY;
 #pragma unroll
   for (int c = 0; c < KC; ++c) {
