@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <random>
@@ -296,8 +297,18 @@ int tw_score_topk(tw_engine* eng, const tw_params* params, const tw_score_out* o
     return fail(TW_ERR_INVALID, "tw_score_topk: used_lo / used_bits / used_wide go together");
   TileList narrow{eng->narrow_tiles, eng->narrow_tiles + eng->n_narrow, eng->n_narrow, kScoreTile};
   TileList wide{eng->wide_tiles, eng->wide_tiles + eng->n_wide, eng->n_wide, kWideThreads - 1};
-  CU(launch_score(eng->dev, params, *out, narrow, wide, eng->prev_idx, eng->narrow_overflow, eng->err_flag,
-                  (cudaStream_t)stream));
+  static const bool use_v1 = getenv("TW_SCORE_V1") != nullptr;   // A/B switch for profiling
+  if (params && !use_v1) {
+    // work-balanced scoring kernel for the narrow tiles; bitmap-overflow tiles are redone by the
+    // wide instantiation of k_score
+    CU(launch_score2(eng->dev, *params, *out, narrow, eng->prev_idx, eng->narrow_overflow, eng->err_flag,
+                     (cudaStream_t)stream));
+    CU(launch_score(eng->dev, params, *out, narrow, wide, eng->prev_idx, eng->narrow_overflow, eng->err_flag,
+                    (cudaStream_t)stream, true));
+  } else {
+    CU(launch_score(eng->dev, params, *out, narrow, wide, eng->prev_idx, eng->narrow_overflow, eng->err_flag,
+                    (cudaStream_t)stream));
+  }
   eng->launches += 2;
   return TW_OK;
 }

@@ -35,7 +35,10 @@ struct TileList {
 cudaError_t launch_prev_index(const tw_batch& b, int32_t* prev_idx, cudaStream_t s);
 cudaError_t launch_score(const tw_batch& b, const tw_params* prm, const tw_score_out& out,
                          const TileList& narrow, const TileList& wide, const int32_t* prev_idx,
-                         uint8_t* narrow_overflow, int* err_flag, cudaStream_t s);
+                         uint8_t* narrow_overflow, int* err_flag, cudaStream_t s, bool wide_only = false);
+cudaError_t launch_score2(const tw_batch& b, const tw_params& prm, const tw_score_out& out,
+                          const TileList& narrow, const int32_t* prev_idx, uint8_t* narrow_overflow,
+                          int* err_flag, cudaStream_t s);
 cudaError_t launch_stitch(const tw_batch& b, const tw_params& prm, const uint8_t* cut,
                           const tw_score_out& spec, const tw_pass_out& out, uint32_t* taken_words, size_t taken_n_words,
                           long long node_limit, int* err_flag, cudaStream_t s);

@@ -356,7 +356,7 @@ k_score(tw_batch b, tw_params prm, int has_params, tw_score_out out, TileList ti
 
 cudaError_t launch_score(const tw_batch& b, const tw_params* prm, const tw_score_out& out,
                          const TileList& narrow, const TileList& wide, const int32_t* prev_idx,
-                         uint8_t* narrow_overflow, int* err_flag, cudaStream_t s) {
+                         uint8_t* narrow_overflow, int* err_flag, cudaStream_t s, bool wide_only) {
   tw_params dummy;
   dummy.mode = TW_PARAMS_MIXTURE; dummy.reserved0 = 0;
   dummy.prob_gauss_off = nullptr; dummy.gauss = nullptr; dummy.mix = nullptr;
@@ -373,12 +373,15 @@ cudaError_t launch_score(const tw_batch& b, const tw_params* prm, const tw_score
     if (e2 != cudaSuccess) return e2;
     attr_done = true;
   }
-  cudaError_t e = cudaMemsetAsync(narrow_overflow, 0, (size_t)narrow.n_tiles, s);
-  if (e != cudaSuccess) return e;
-  kn<<<narrow.n_tiles, kScoreThreads, sizeof(SmN), s>>>(b, pr, prm != nullptr, out, narrow, prev_idx,
-                                                        narrow_overflow, 0, err_flag);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
+  cudaError_t e = cudaSuccess;
+  if (!wide_only) {   // otherwise k_score2 has run the narrow tiles and set the overflow flags
+    e = cudaMemsetAsync(narrow_overflow, 0, (size_t)narrow.n_tiles, s);
+    if (e != cudaSuccess) return e;
+    kn<<<narrow.n_tiles, kScoreThreads, sizeof(SmN), s>>>(b, pr, prm != nullptr, out, narrow, prev_idx,
+                                                          narrow_overflow, 0, err_flag);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
   kw<<<wide.n_tiles, kWideThreads, sizeof(SmW), s>>>(b, pr, prm != nullptr, out, wide, prev_idx,
                                                      narrow_overflow, 1, err_flag);
   return cudaGetLastError();
