@@ -45,7 +45,9 @@ struct Score2Smem {
   int rcount[T], nfeas[T];
   int scan_a[T / 32], scan_b[T / 32];
   int win_a[TW_MAX_E], win_n[TW_MAX_E];
-  int staged, overflow, rc, n_ent, total_t, total_c, first_tid, last_tid;
+  int staged, overflow, rc, n_ent, total_t, total_c, first_tid, last_tid, stream_tid, n_carry;
+  unsigned long long carry_key[TW_K];
+  uint32_t carry_combo[TW_K];
   uint16_t ent_j[kEnt2];
   uint8_t sid[kTbl2];
   uint8_t tie[T];
@@ -224,25 +226,36 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
       if (lane >= d) { inc_t += ot; inc_c += oc; }
     }
     if (lane == 31) { sm.scan_a[wid] = inc_t; sm.scan_b[wid] = inc_c; }
-    if (tid == 0) { sm.total_t = 0; sm.total_c = 0; sm.first_tid = T; sm.last_tid = -1; sm.n_ent = 0; }
+    if (tid == 0) {
+      sm.total_t = 0; sm.total_c = 0; sm.first_tid = T; sm.last_tid = -1; sm.n_ent = 0;
+      sm.stream_tid = -1; sm.n_carry = 0;
+    }
     __syncthreads();
     int toff = inc_t - my_t, coff = inc_c - my_c;
     for (int q = 0; q < wid; ++q) { toff += sm.scan_a[q]; coff += sm.scan_b[q]; }
     const bool fits = pending && toff + my_t <= kTbl2 && coff + my_c <= kEnt2;
-    // the first pending in-span always makes progress: sequential walk if it can never fit
-    const bool first_pending = pending && (toff == 0 && coff == 0) && (tsize > kTbl2 || P > kEnt2);
-    const bool in_round = fits && !first_pending;
+    // The first pending in-span always makes progress.  More combinations than list entries: it
+    // takes the round alone and its combinations are STREAMED through the list in chunks, the
+    // running top-K carried from chunk to chunk.  Tables that cannot fit: sequential walk.
+    const bool first_pending = pending && toff == 0 && coff == 0;
+    const bool can_stream = tsize <= kTbl2 && P > kEnt2 && P < (1LL << 31);
+    const bool stream = first_pending && can_stream;
+    const bool serial = first_pending && !can_stream && (tsize > kTbl2 || P > kEnt2);
+    const bool in_round = stream || (fits && !serial);
     sm.tstart[tid] = in_round ? toff : 0x3fffffff;
     sm.cstart[tid] = in_round ? coff : 0x3fffffff;
     if (in_round) {
       atomicMax(&sm.total_t, toff + my_t);
-      atomicMax(&sm.total_c, coff + my_c);
+      atomicMax(&sm.total_c, stream ? (int)P : coff + my_c);
       atomicMin(&sm.first_tid, tid);
       atomicMax(&sm.last_tid, tid);
     }
-    if (first_pending) { serial_walk(); pending = false; }
+    if (stream) sm.stream_tid = tid;
+    if (serial) { serial_walk(); pending = false; }
     __syncthreads();
     const int total_t = sm.total_t, total_c = sm.total_c, f_tid = sm.first_tid, l_tid = sm.last_tid;
+    const int stream_tid = sm.stream_tid;
+    const int chunk = stream_tid >= 0 ? kEnt2 - TW_K : 0x7fffffff;
     auto owner_of = [&](const int* start, int item) {   // last in-round tid with start <= item
       int a = f_tid, z = l_tid + 1;
       while (a < z) {
@@ -269,63 +282,82 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
       sm.tbl[s] = val;
     }
     __syncthreads();
-    // ---- 2. combinations: feasibility, score, list entry, candidate bitmap
-    for (int g = tid; g < total_c; g += T) {
-      const int j = owner_of(sm.cstart, g);
-      int lo_rel[TW_MAX_E], o_last[TW_MAX_E], c[TW_MAX_E];
-      int64_t ce[TW_MAX_E];
-      for (int e = 0; e < E; ++e) lo_rel[e] = sm.lo_abs[j][e] - sm.win[e].base;
-      term_table_last_offsets(v, sm.rr[j], o_last);
-      const int combo = g - sm.cstart[j];
-      const double* tbl = sm.tbl + sm.tstart[j];
-      if (!combo_feasible(v, sm.win, lo_rel, sm.rr[j], o_last, sm.sid + sm.tstart[j], combo, c, ce)) continue;
-      atomicAdd(&sm.nfeas[j], 1);
-      for (int e = 0; e < E; ++e) {
-        int bit = c[e] - sm.lo_abs[j][e];
-        if (bit >= 32 * W) sm.overflow = 1;
-        else atomicOr(&sm.used[j][e][bit >> 5], 1u << (bit & 31));
+    // ---- 2 + 3 per chunk of combinations (one chunk unless an in-span is being streamed)
+    for (long long cbase = 0; cbase == 0 || cbase < total_c; cbase += chunk) {
+      const int cend = (int)(cbase + chunk < (long long)total_c ? cbase + chunk : (long long)total_c);
+      if (cbase > 0) {   // streaming: the running top-K re-enters the list
+        if (tid < sm.n_carry) {
+          sm.ent_key[tid] = sm.carry_key[tid];
+          sm.ent_combo[tid] = sm.carry_combo[tid];
+          sm.ent_j[tid] = (uint16_t)stream_tid;
+        }
+        if (tid == 0) sm.n_ent = sm.n_carry;
+        __syncthreads();
       }
-      unsigned long long key = score_key(table_score(v, sm.rr[j], sm.lo_abs[j], tbl, c, ce));
-      if (key == 0ULL) key = 1ULL;
-      const int slot = atomicAdd(&sm.n_ent, 1);
-      sm.ent_key[slot] = key;
-      sm.ent_combo[slot] = (uint32_t)combo;
-      sm.ent_j[slot] = (uint16_t)j;
-    }
-    __syncthreads();
-    // ---- 3. top-K: K rounds of segmented arg-max over the list
-    const int n_ent = sm.n_ent;
-    for (int rk = 0; rk < TW_K; ++rk) {
-      bool any = false;
-      for (int en = tid; en < n_ent; en += T) {
-        const unsigned long long key = sm.ent_key[en];
-        if (key != 0ULL) { atomicMax(&sm.rbest[sm.ent_j[en]], key); any = true; }
+      // ---- 2. combinations: feasibility, score, list entry, candidate bitmap
+      for (int g = (int)cbase + tid; g < cend; g += T) {
+        const int j = stream_tid >= 0 ? stream_tid : owner_of(sm.cstart, g);
+        int lo_rel[TW_MAX_E], o_last[TW_MAX_E], c[TW_MAX_E];
+        int64_t ce[TW_MAX_E];
+        for (int e = 0; e < E; ++e) lo_rel[e] = sm.lo_abs[j][e] - sm.win[e].base;
+        term_table_last_offsets(v, sm.rr[j], o_last);
+        const int combo = g - sm.cstart[j];
+        const double* tbl = sm.tbl + sm.tstart[j];
+        if (!combo_feasible(v, sm.win, lo_rel, sm.rr[j], o_last, sm.sid + sm.tstart[j], combo, c, ce)) continue;
+        atomicAdd(&sm.nfeas[j], 1);
+        for (int e = 0; e < E; ++e) {
+          int bit = c[e] - sm.lo_abs[j][e];
+          if (bit >= 32 * W) sm.overflow = 1;
+          else atomicOr(&sm.used[j][e][bit >> 5], 1u << (bit & 31));
+        }
+        unsigned long long key = score_key(table_score(v, sm.rr[j], sm.lo_abs[j], tbl, c, ce));
+        if (key == 0ULL) key = 1ULL;
+        const int slot = atomicAdd(&sm.n_ent, 1);
+        sm.ent_key[slot] = key;
+        sm.ent_combo[slot] = (uint32_t)combo;
+        sm.ent_j[slot] = (uint16_t)j;
       }
-      if (!__syncthreads_or(any)) break;
-      for (int en = tid; en < n_ent; en += T) {
-        const unsigned long long key = sm.ent_key[en];
-        const int j = sm.ent_j[en];
-        if (key != 0ULL && key == sm.rbest[j]) {
-          if (atomicAdd(&sm.rcount[j], 1) == 0) {   // winner of rank rk for in-span j
-            sm.ent_key[en] = 0ULL;
-            const int ij = i0 + j;
-            const int64_t gi = v.in_off + ij;
-            out.topk_score[gi * TW_K + rk] = key_to_score(key);
-            int32_t* ix = out.topk_idx + TW_K * (v.tuple_off + (int64_t)ij * E) + rk * E;
-            long long idx = sm.ent_combo[en];
-            for (int e = E - 1; e >= 0; --e) {
-              const int re = sm.rr[j][e];
-              ix[e] = sm.lo_abs[j][e] + (int)(idx % re);
-              idx /= re;
+      __syncthreads();
+      // ---- 3. top-K: K rounds of segmented arg-max over the list
+      const int n_ent = sm.n_ent;
+      int ranks_done = 0;
+      for (int rk = 0; rk < TW_K; ++rk) {
+        bool any = false;
+        for (int en = tid; en < n_ent; en += T) {
+          const unsigned long long key = sm.ent_key[en];
+          if (key != 0ULL) { atomicMax(&sm.rbest[sm.ent_j[en]], key); any = true; }
+        }
+        if (!__syncthreads_or(any)) break;
+        ranks_done = rk + 1;
+        for (int en = tid; en < n_ent; en += T) {
+          const unsigned long long key = sm.ent_key[en];
+          const int j = sm.ent_j[en];
+          if (key != 0ULL && key == sm.rbest[j]) {
+            if (atomicAdd(&sm.rcount[j], 1) == 0) {   // winner of rank rk for in-span j
+              sm.ent_key[en] = 0ULL;
+              const int ij = i0 + j;
+              const int64_t gi = v.in_off + ij;
+              out.topk_score[gi * TW_K + rk] = key_to_score(key);
+              int32_t* ix = out.topk_idx + TW_K * (v.tuple_off + (int64_t)ij * E) + rk * E;
+              long long idx = sm.ent_combo[en];
+              for (int e = E - 1; e >= 0; --e) {
+                const int re = sm.rr[j][e];
+                ix[e] = sm.lo_abs[j][e] + (int)(idx % re);
+                idx /= re;
+              }
+              if (stream_tid >= 0) { sm.carry_key[rk] = key; sm.carry_combo[rk] = sm.ent_combo[en]; }
+            } else {
+              sm.tie[j] = 1;   // two tuples with the same score: keep the reference's tie order
             }
-          } else {
-            sm.tie[j] = 1;   // two tuples with the same score: keep the reference's tie order
           }
         }
+        __syncthreads();
+        if (in_round) { sm.rbest[tid] = 0ULL; sm.rcount[tid] = 0; }
+        __syncthreads();
       }
+      if (tid == 0) sm.n_carry = ranks_done;
       __syncthreads();
-      if (in_round) { sm.rbest[tid] = 0ULL; sm.rcount[tid] = 0; }
-      __syncthreads();
+      if (chunk == 0x7fffffff) break;
     }
     // ---- owners finish their in-span
     if (in_round) {
