@@ -397,7 +397,7 @@ int tw_gmm_refit(tw_engine* eng, const int64_t* term_sample_off, const double* d
   CU(launch_gmm_fit(nt, term_sample_off, delays, counts, eng->gmm_max_n, eng->gmm_mean_var, eng->gmm_skip,
                     eng->gmm_stream, tw_engine::kStreamLen, eng->gmm_stream100, eng->gmm_bic, mix_out,
                     n_selected_out, eng->err_flag, s));
-  eng->launches += 4;
+  eng->launches += 12;   // prep, skip, 5 x bic, 5 x final
   return TW_OK;
 }
 

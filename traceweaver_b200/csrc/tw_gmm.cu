@@ -67,7 +67,7 @@ __device__ __forceinline__ int nearest(const double* cen, int k, double x) {
 
 // KMeans(n_clusters=k, n_init=1).fit(X): returns the centres (on centred data) that define the
 // final labels_.  draws[] = this fit's random_sample() values.
-__device__ void kmeans_label_centers(const double* __restrict__ x, int n, int k, double mean, double tol,
+__device__ __forceinline__ void kmeans_label_centers(const double* __restrict__ x, int n, int k, double mean, double tol,
                                      const double* __restrict__ draws, double* cen_out) {
   const int lane = threadIdx.x & 31;
   double cen[KC];
@@ -290,7 +290,7 @@ __device__ __forceinline__ double estep(const Fit& f, int k, double x, double* a
 // Returns false on scikit-learn's ValueError paths; *score = mean log-likelihood under the final
 // parameters when want_score.
 template <bool FULL>
-__device__ bool warp_fit(const double* __restrict__ x, int n, int k, double mean, double tol,
+__device__ __forceinline__ bool warp_fit(const double* __restrict__ x, int n, int k, double mean, double tol,
                          const double* __restrict__ draws, Fit& f, bool want_score, double* score) {
   const int lane = threadIdx.x & 31;
   if (n < 2 || n < k) return false;
@@ -471,35 +471,42 @@ __global__ void k_gmm_draws(int n_problems, const int32_t* __restrict__ prob_ep_
   prob_draws[p] = pos;
 }
 
-__global__ void __launch_bounds__(128, 5)
+// One kernel instance per component count K: with K a compile-time constant every `c < k` test
+// and component loop of warp_fit folds away, registers hold exactly K components, and all warps of
+// an SM run the same (small) loop bodies, which keeps them in the instruction cache — the
+// single generic kernel of round 1 lost half its issue slots to instruction fetch (stall_no_inst).
+template <int K>
+__global__ void __launch_bounds__(128)
 k_gmm_bic(int n_terms, const int64_t* __restrict__ term_sample_off, const double* __restrict__ delays,
           const int32_t* __restrict__ counts, const int32_t* __restrict__ max_n,
           const double* __restrict__ mean_var, const uint32_t* __restrict__ rng_skip,
           const double* __restrict__ stream, int stream_len, double* __restrict__ bic_out,
           int* __restrict__ err_flag) {
-  const int wid = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
-  if (wid >= n_terms * KC) return;
-  const int t = wid / KC, k = wid % KC + 1;
+  const int t = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (t >= n_terms) return;
   const int lane = threadIdx.x & 31;
   double bic = INFINITY;
   const int n = counts[t];
-  if (k <= max_n[t]) {
+  if (K <= max_n[t]) {
     uint32_t pos = rng_skip[t];
-    for (int q = 1; q < k; ++q) pos += (uint32_t)draws_for_k(q);
-    if ((int)pos + draws_for_k(k) > stream_len) {
+#pragma unroll
+    for (int q = 1; q < K; ++q) pos += (uint32_t)draws_for_k(q);
+    if ((int)pos + draws_for_k(K) > stream_len) {
       if (lane == 0) atomicMin(err_flag, (int)TW_ERR_RANGE_LIMIT);
     } else {
       Fit f;
       double sc = 0.0;
       const double* x = delays + term_sample_off[t];
-      if (warp_fit<false>(x, n, k, mean_var[2 * t], mean_var[2 * t + 1] * kKmTol, stream + pos, f, true, &sc))
-        bic = -2.0 * sc * (double)n + (double)(3 * k - 1) * log((double)n);   // GaussianMixture.bic, 'diag'
+      if (warp_fit<false>(x, n, K, mean_var[2 * t], mean_var[2 * t + 1] * kKmTol, stream + pos, f, true, &sc))
+        bic = -2.0 * sc * (double)n + (double)(3 * K - 1) * log((double)n);   // GaussianMixture.bic, 'diag'
     }
   }
-  if (lane == 0) bic_out[(size_t)t * KC + (k - 1)] = bic;
+  if (lane == 0) bic_out[(size_t)t * KC + (K - 1)] = bic;
 }
 
-__global__ void __launch_bounds__(128, 5)
+// final 'full' fit of the terms whose BIC arg-min is K (K == 1 also writes the no-fit records)
+template <int K>
+__global__ void __launch_bounds__(128)
 k_gmm_final(int n_terms, const int64_t* __restrict__ term_sample_off, const double* __restrict__ delays,
             const int32_t* __restrict__ counts, const int32_t* __restrict__ max_n,
             const double* __restrict__ mean_var, const double* __restrict__ bic,
@@ -515,17 +522,19 @@ k_gmm_final(int n_terms, const int64_t* __restrict__ term_sample_off, const doub
     double b = bic[(size_t)t * KC + (k - 1)];
     if (b < best) { best = b; best_k = k; }
   }
+  if (best_k != K && !(K == 1 && best_k == 0)) return;
   Fit f;
   bool ok = false;
-  if (best_k > 0)
-    ok = warp_fit<true>(delays + term_sample_off[t], n, best_k, mean_var[2 * t], mean_var[2 * t + 1] * kKmTol,
+  if (best_k == K)
+    ok = warp_fit<true>(delays + term_sample_off[t], n, K, mean_var[2 * t], mean_var[2 * t + 1] * kKmTol,
                         stream100, f, false, nullptr);
   if (lane == 0) {
     double* rec = mix_out + (size_t)t * TW_MIX_REC;
     for (int q = 0; q < TW_MIX_REC; ++q) rec[q] = 0.0;
     if (ok) {
-      rec[0] = (double)best_k;
-      for (int c = 0; c < best_k; ++c) {
+      rec[0] = (double)K;
+#pragma unroll
+      for (int c = 0; c < K; ++c) {
         rec[1 + c] = f.pc[c];
         rec[6 + c] = f.mu[c] * f.pc[c];
         rec[11 + c] = f.logpc[c];
@@ -535,7 +544,7 @@ k_gmm_final(int n_terms, const int64_t* __restrict__ term_sample_off, const doub
       rec[2] = 0.001;
       rec[3] = log(0.001);
     }
-    if (n_selected_out) n_selected_out[t] = ok ? best_k : 0;
+    if (n_selected_out) n_selected_out[t] = ok ? K : 0;
   }
 }
 
@@ -559,19 +568,36 @@ cudaError_t launch_gmm_draws(int n_problems, const int32_t* prob_ep_off, const i
   return cudaGetLastError();
 }
 
+template <int K>
+static cudaError_t launch_gmm_k(int n_terms, const int64_t* term_sample_off, const double* delays,
+                                const int32_t* counts, const int32_t* max_n, const double* mean_var,
+                                const uint32_t* rng_skip, const double* stream, int stream_len, double* bic,
+                                int* err_flag, cudaStream_t s) {
+  k_gmm_bic<K><<<(n_terms + 3) / 4, 128, 0, s>>>(n_terms, term_sample_off, delays, counts, max_n, mean_var,
+                                                 rng_skip, stream, stream_len, bic, err_flag);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_gmm_fit(int n_terms, const int64_t* term_sample_off, const double* delays,
                            const int32_t* counts, const int32_t* max_n, const double* mean_var,
                            const uint32_t* rng_skip, const double* stream, int stream_len,
                            const double* stream100, double* bic, double* mix_out, int32_t* n_selected_out,
                            int* err_flag, cudaStream_t s) {
-  int warps = n_terms * KC;
-  k_gmm_bic<<<(warps + 3) / 4, 128, 0, s>>>(n_terms, term_sample_off, delays, counts, max_n, mean_var, rng_skip,
-                                            stream, stream_len, bic, err_flag);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e;
+#define TW_BIC(K)                                                                                        \
+  e = launch_gmm_k<K>(n_terms, term_sample_off, delays, counts, max_n, mean_var, rng_skip, stream, stream_len, \
+                      bic, err_flag, s);                                                                 \
   if (e != cudaSuccess) return e;
-  k_gmm_final<<<(n_terms + 3) / 4, 128, 0, s>>>(n_terms, term_sample_off, delays, counts, max_n, mean_var, bic,
-                                                stream100, mix_out, n_selected_out);
-  return cudaGetLastError();
+  TW_BIC(5) TW_BIC(4) TW_BIC(3) TW_BIC(2) TW_BIC(1)     // longest fits first
+#undef TW_BIC
+#define TW_FINAL(K)                                                                                      \
+  k_gmm_final<K><<<(n_terms + 3) / 4, 128, 0, s>>>(n_terms, term_sample_off, delays, counts, max_n, mean_var, \
+                                                   bic, stream100, mix_out, n_selected_out);             \
+  e = cudaGetLastError();                                                                                \
+  if (e != cudaSuccess) return e;
+  TW_FINAL(5) TW_FINAL(4) TW_FINAL(3) TW_FINAL(2) TW_FINAL(1)
+#undef TW_FINAL
+  return cudaSuccess;
 }
 
 }  // namespace tw
