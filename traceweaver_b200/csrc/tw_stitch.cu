@@ -21,6 +21,7 @@ struct StitchWarpSmem {
   ProbView v;
   WindowBuf wb;
   double tbl[kWarpTblCap];     // term tables of the current window (tw_core.cuh)
+  uint32_t tk[kTakenWords];    // taken bitmap of the service when it fits (else global memory)
   uint8_t sid[kWarpTblCap];
 };
 
@@ -49,10 +50,23 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
   // taken bitmap of (problem, ep): word-aligned region, see tw_api.cu (taken_words)
   uint32_t* tk_base[TW_MAX_E];
   OutWin w[TW_MAX_E];
-  for (int e = 0; e < E; ++e) {
-    tk_base[e] = taken + (v.out_off[e] >> 5) + (v.ep0 + e);
-    w[e].s = v.os[e]; w[e].e = v.oe[e]; w[e].base = 0; w[e].n = v.n_out[e];
+  // The taken bitmap lives in this warp's shared memory when the service is small enough (the
+  // fast-path test then costs no L2 round trip per window); +2 words of slack per ep because the
+  // test reads three consecutive words.
+  int tk_words = 0;
+  for (int e = 0; e < E; ++e) tk_words += (v.n_out[e] >> 5) + 3;
+  const bool tk_smem = tk_words <= kTakenWords;
+  {
+    int off = 0;
+    for (int e = 0; e < E; ++e) {
+      tk_base[e] = tk_smem ? sm.tk + off : taken + (v.out_off[e] >> 5) + (v.ep0 + e);
+      off += (v.n_out[e] >> 5) + 3;
+      w[e].s = v.os[e]; w[e].e = v.oe[e]; w[e].base = 0; w[e].n = v.n_out[e];
+    }
   }
+  if (tk_smem)
+    for (int x = lane; x < tk_words; x += 32) sm.tk[x] = 0u;
+  __syncwarp();
   // defaults
   for (int i = lane; i < n; i += 32) out.mis_rank[v.in_off + i] = -1;
   for (int64_t x = lane; x < (int64_t)n * E; x += 32) out.assign[v.tuple_off + x] = -1;
@@ -242,7 +256,7 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
     }
     not_best += __popc(__ballot_sync(0xffffffffu, lane < nw && rank != 0));
     unassigned += __popc(__ballot_sync(0xffffffffu, lane < nw && rank < 0));
-    __threadfence_block();
+    if (!tk_smem) __threadfence_block();
     __syncwarp();
     ws = we + 1;
   }
