@@ -203,7 +203,8 @@ def run_ours(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "score_traffic.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"kernel": "k_score<128,2> (GMM pass, final top-K)", "bound": "hbm", "achieved": round(achieved, 2),
+    roofline = {"kernel": "k_score2<128> (+ k_score<32,64> overflow redo): GMM pass, final top-K", "bound": "hbm",
+                "achieved": round(achieved, 2),
                 "peak": peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
                 "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": round(score_ms, 4)}
