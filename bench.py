@@ -200,7 +200,8 @@ def run_ours(args):
     achieved = alg_bytes / (score_ms * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "score_traffic.json"))).get("dram_bytes_per_launch")
+        per = json.load(open(os.path.join(ROOT, "profiles", "score_traffic.json"))).get("dram_bytes_per_in_span")
+        traffic = int(per * int(n_of.sum())) if per else None   # ncu capture scaled to this launch's in-spans
     except Exception:
         pass
     roofline = {"kernel": "k_score2<128> (+ k_score<32,64> overflow redo): GMM pass, final top-K", "bound": "hbm",
