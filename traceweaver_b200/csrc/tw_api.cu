@@ -359,7 +359,7 @@ static int gmm_prepare(tw_engine* eng, uint32_t seed_select, cudaStream_t s) {
   const int nt = eng->dev.n_term_total;
   CU(eng->alloc(&eng->gmm_max_n, (size_t)nt));
   CU(eng->alloc(&eng->gmm_mean_var, (size_t)nt * 2));
-  CU(eng->alloc(&eng->gmm_skip, (size_t)nt));
+  CU(eng->alloc(&eng->gmm_skip, (size_t)nt + 64));   // + histogram / cursors of the final-fit grouping
   CU(eng->alloc(&eng->gmm_bic, (size_t)nt * TW_GMM_MAX_COMP));
   CU(eng->alloc(&eng->gmm_stream, (size_t)tw_engine::kStreamLen));
   CU(eng->alloc(&eng->gmm_stream100, 16));
@@ -397,7 +397,7 @@ int tw_gmm_refit(tw_engine* eng, const int64_t* term_sample_off, const double* d
   CU(launch_gmm_fit(nt, term_sample_off, delays, counts, eng->gmm_max_n, eng->gmm_mean_var, eng->gmm_skip,
                     eng->gmm_stream, tw_engine::kStreamLen, eng->gmm_stream100, eng->gmm_bic, mix_out,
                     n_selected_out, eng->err_flag, s));
-  eng->launches += 12;   // prep, skip, 5 x bic, 5 x final
+  eng->launches += 14;   // prep, skip, 5 x bic, select, group, 5 x final
   return TW_OK;
 }
 

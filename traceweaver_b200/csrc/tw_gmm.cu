@@ -504,30 +504,62 @@ k_gmm_bic(int n_terms, const int64_t* __restrict__ term_sample_off, const double
   if (lane == 0) bic_out[(size_t)t * KC + (K - 1)] = bic;
 }
 
-// final 'full' fit of the terms whose BIC arg-min is K (K == 1 also writes the no-fit records)
-template <int K>
-__global__ void __launch_bounds__(128)
-k_gmm_final(int n_terms, const int64_t* __restrict__ term_sample_off, const double* __restrict__ delays,
-            const int32_t* __restrict__ counts, const int32_t* __restrict__ max_n,
-            const double* __restrict__ mean_var, const double* __restrict__ bic,
-            const double* __restrict__ stream100, double* __restrict__ mix_out,
-            int32_t* __restrict__ n_selected_out) {
-  const int t = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+// np.argmin over the BICs of the fits that did not raise (first minimum); terms without a fit get
+// the degenerate record right here: services_times = (0, 0) -> sigma clamp (V3:765-766, V1:130-131).
+// hist[k] counts the terms whose arg-min is k.
+__global__ void k_gmm_select(int n_terms, const int32_t* __restrict__ max_n, const double* __restrict__ bic,
+                             int32_t* __restrict__ best_k_out, uint32_t* __restrict__ hist,
+                             double* __restrict__ mix_out, int32_t* __restrict__ n_selected_out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_terms) return;
-  const int lane = threadIdx.x & 31;
-  const int n = counts[t];
   int best_k = 0;
   double best = INFINITY;
-  for (int k = 1; k <= max_n[t]; ++k) {     // np.argmin over the fits that did not raise: first minimum
+  for (int k = 1; k <= max_n[t]; ++k) {
     double b = bic[(size_t)t * KC + (k - 1)];
     if (b < best) { best = b; best_k = k; }
   }
-  if (best_k != K && !(K == 1 && best_k == 0)) return;
+  best_k_out[t] = best_k;
+  if (best_k > 0) atomicAdd(&hist[best_k], 1u);
+  else {
+    double* rec = mix_out + (size_t)t * TW_MIX_REC;
+    for (int q = 0; q < TW_MIX_REC; ++q) rec[q] = 0.0;
+    rec[2] = 0.001;
+    rec[3] = log(0.001);
+    if (n_selected_out) n_selected_out[t] = 0;
+  }
+}
+
+// terms grouped by their arg-min K: list[off_K + j], off_K = hist[1] + ... + hist[K-1]
+__global__ void k_gmm_group(int n_terms, const int32_t* __restrict__ best_k, const uint32_t* __restrict__ hist,
+                            uint32_t* __restrict__ cursor, int32_t* __restrict__ list) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_terms) return;
+  const int k = best_k[t];
+  if (k <= 0) return;
+  uint32_t off = 0;
+  for (int q = 1; q < k; ++q) off += hist[q];
+  list[off + atomicAdd(&cursor[k], 1u)] = t;
+}
+
+// final 'full' fit of the terms whose BIC arg-min is K: dense warps over the grouped list
+template <int K>
+__global__ void __launch_bounds__(128)
+k_gmm_final(const int32_t* __restrict__ list, const uint32_t* __restrict__ hist,
+            const int64_t* __restrict__ term_sample_off, const double* __restrict__ delays,
+            const int32_t* __restrict__ counts, const double* __restrict__ mean_var,
+            const double* __restrict__ stream100, double* __restrict__ mix_out,
+            int32_t* __restrict__ n_selected_out) {
+  const unsigned w = (blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5;
+  if (w >= hist[K]) return;
+  uint32_t off = 0;
+#pragma unroll
+  for (int q = 1; q < K; ++q) off += hist[q];
+  const int t = list[off + w];
+  const int lane = threadIdx.x & 31;
+  const int n = counts[t];
   Fit f;
-  bool ok = false;
-  if (best_k == K)
-    ok = warp_fit<true>(delays + term_sample_off[t], n, K, mean_var[2 * t], mean_var[2 * t + 1] * kKmTol,
-                        stream100, f, false, nullptr);
+  const bool ok = warp_fit<true>(delays + term_sample_off[t], n, K, mean_var[2 * t], mean_var[2 * t + 1] * kKmTol,
+                                 stream100, f, false, nullptr);
   if (lane == 0) {
     double* rec = mix_out + (size_t)t * TW_MIX_REC;
     for (int q = 0; q < TW_MIX_REC; ++q) rec[q] = 0.0;
@@ -540,7 +572,7 @@ k_gmm_final(int n_terms, const int64_t* __restrict__ term_sample_off, const doub
         rec[11 + c] = f.logpc[c];
         rec[16 + c] = f.logw[c];
       }
-    } else {   // no samples / no fit: services_times = (0, 0) -> sigma clamp (V3:765-766, V1:130-131)
+    } else {
       rec[2] = 0.001;
       rec[3] = log(0.001);
     }
@@ -590,9 +622,24 @@ cudaError_t launch_gmm_fit(int n_terms, const int64_t* term_sample_off, const do
   if (e != cudaSuccess) return e;
   TW_BIC(5) TW_BIC(4) TW_BIC(3) TW_BIC(2) TW_BIC(1)     // longest fits first
 #undef TW_BIC
+  // group the terms by selected K so that the final fits run with every warp busy.  Scratch:
+  // rng_skip (free after the BIC fits) -> hist[0..7], cursor[8..15]; bic (free after the select
+  // kernel) -> the grouped list; max_n -> best_k.
+  uint32_t* hist = const_cast<uint32_t*>(rng_skip);
+  uint32_t* cursor = hist + 8;
+  int32_t* best_k = const_cast<int32_t*>(max_n);
+  int32_t* list = reinterpret_cast<int32_t*>(bic);
+  e = cudaMemsetAsync(hist, 0, 16 * sizeof(uint32_t), s);
+  if (e != cudaSuccess) return e;
+  k_gmm_select<<<(n_terms + 127) / 128, 128, 0, s>>>(n_terms, max_n, bic, best_k, hist, mix_out, n_selected_out);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  k_gmm_group<<<(n_terms + 127) / 128, 128, 0, s>>>(n_terms, best_k, hist, cursor, list);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
 #define TW_FINAL(K)                                                                                      \
-  k_gmm_final<K><<<(n_terms + 3) / 4, 128, 0, s>>>(n_terms, term_sample_off, delays, counts, max_n, mean_var, \
-                                                   bic, stream100, mix_out, n_selected_out);             \
+  k_gmm_final<K><<<(n_terms + 3) / 4, 128, 0, s>>>(list, hist, term_sample_off, delays, counts, mean_var, \
+                                                   stream100, mix_out, n_selected_out);                  \
   e = cudaGetLastError();                                                                                \
   if (e != cudaSuccess) return e;
   TW_FINAL(5) TW_FINAL(4) TW_FINAL(3) TW_FINAL(2) TW_FINAL(1)
