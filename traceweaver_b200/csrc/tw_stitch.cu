@@ -22,6 +22,7 @@ struct StitchWarpSmem {
   WindowBuf wb;
   double tbl[kWarpTblCap];     // term tables of the current window (tw_core.cuh)
   uint32_t tk[kTakenWords];    // taken bitmap of the service when it fits (else global memory)
+  uint32_t tmp[kTakenWords];   // scratch bitmap of the run path (always left zero)
   uint8_t sid[kWarpTblCap];
 };
 
@@ -65,7 +66,7 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
     }
   }
   if (tk_smem)
-    for (int x = lane; x < tk_words; x += 32) sm.tk[x] = 0u;
+    for (int x = lane; x < tk_words; x += 32) { sm.tk[x] = 0u; sm.tmp[x] = 0u; }
   __syncwarp();
   // defaults
   for (int i = lane; i < n; i += 32) out.mis_rank[v.in_off + i] = -1;
@@ -80,7 +81,83 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
   int not_best = 0, unassigned = 0;
   long long max_nodes = 0;
   int ws = 0;
+  bool skip_run = false;
+  const bool can_run = tk_smem && spec.used_lo != nullptr && out.topk_score == nullptr;
   while (ws < n) {
+    // ---- run of consecutive ONE-in-span windows, one lane each.  Windows only interact through
+    // the taken bits, so if (a) every in-span of the run passes the fast-path test against the bits
+    // taken so far and (b) the candidate maps of the run are pairwise disjoint, processing them
+    // one after the other would give every one of them its undeleted rank-0 tuple: commit them
+    // together.  Anything else falls back to the window-at-a-time path below (same results).
+    if (can_run && !skip_run) {
+      WindowCursor wc2 = wc, wc_ok = wc;
+      int R = 0;
+      while (R < 32 && ws + R < n) {
+        if (!wc2.ends_at(ws + R, n, cut)) break;   // window continues past this in-span
+        wc_ok = wc2;
+        ++R;
+      }
+      if (R >= 1) {
+        const bool act = lane < R;
+        const int ir = ws + (act ? lane : 0);
+        const int64_t gi = v.in_off + ir;
+        const int64_t base = v.tuple_off + (int64_t)ir * E;
+        bool ok = act ? spec.used_wide[gi] == 0 : true;
+        if (act && ok) {
+          for (int e = 0; e < E; ++e) {
+            const int ulo = spec.used_lo[base + e];
+            const uint32_t u0 = spec.used_bits[2 * (base + e)], u1 = spec.used_bits[2 * (base + e) + 1];
+            if ((u0 | u1) == 0u) continue;
+            const int q = ulo >> 5, sh = ulo & 31;
+            // the map in the coordinates of the taken bitmap: three words
+            const uint32_t m0 = u0 << sh;
+            const uint32_t m1 = sh ? (u0 >> (32 - sh)) | (u1 << sh) : u1;
+            const uint32_t m2 = sh ? (u1 >> (32 - sh)) : 0u;
+            uint32_t* tkp = tk_base[e] + q;
+            uint32_t* tmp = sm.tmp + (tkp - sm.tk);
+            if ((tkp[0] & m0) | (tkp[1] & m1) | (tkp[2] & m2)) ok = false;          // (a)
+            if (m0 && (atomicOr(&tmp[0], m0) & m0)) ok = false;                     // (b)
+            if (m1 && (atomicOr(&tmp[1], m1) & m1)) ok = false;
+            if (m2 && (atomicOr(&tmp[2], m2) & m2)) ok = false;
+          }
+        }
+        const bool all_ok = __all_sync(0xffffffffu, ok);
+        __syncwarp();
+        if (act && spec.used_wide[gi] == 0) {   // leave the scratch bitmap zero for the next run
+          for (int e = 0; e < E; ++e) {
+            const int ulo = spec.used_lo[base + e];
+            uint32_t* tmp = sm.tmp + ((tk_base[e] + (ulo >> 5)) - sm.tk);
+            tmp[0] = 0u; tmp[1] = 0u; tmp[2] = 0u;
+          }
+        }
+        __syncwarp();
+        if (all_ok) {
+          int rank = -2;
+          if (act) {
+            const int cnt = spec.topk_cnt[gi];
+            rank = (cnt > 0 && TW_WEIGHT_OFFSET + spec.topk_score[gi * TW_K] > 0.0) ? 0 : -1;
+            out.n_cand[gi] = spec.n_feasible[gi];
+            out.mis_rank[gi] = (int8_t)rank;
+            if (rank == 0) {
+              const int32_t* ix = spec.topk_idx + TW_K * base;
+              for (int e = 0; e < E; ++e) {
+                const int o = ix[e];
+                out.assign[v.tuple_off + (int64_t)e * n + ir] = o;
+                atomicOr(&tk_base[e][o >> 5], 1u << (o & 31));
+              }
+            }
+          }
+          unassigned += __popc(__ballot_sync(0xffffffffu, act && rank < 0));
+          not_best += __popc(__ballot_sync(0xffffffffu, act && rank != 0));
+          __syncwarp();
+          wc = wc_ok;
+          ws += R;
+          continue;
+        }
+        skip_run = true;   // conflict: do this window the long way, then try runs again
+      }
+    }
+    skip_run = false;
     // ---- window extent (uniform across the warp)
     int we = ws;
     while (!wc.ends_at(we, n, cut) && we < n - 1) ++we;
