@@ -403,7 +403,9 @@ static int mw_conflict(const mwis_t* m, int a, int ra, int bq, int rb) {
     if (m->cand[a].h[ra].c[e] == m->cand[bq].h[rb].c[e]) return 1;
   return 0;
 }
+#define TWO_MWIS_NODE_LIMIT 20000000LL /* give up loudly instead of searching for hours */
 static void mw_rec(mwis_t* m, int k, double cur_w) {
+  if (m->nodes > TWO_MWIS_NODE_LIMIT) return;
   m->nodes++;
   if (k == m->nw) {
     if (cur_w > m->best_w) { m->best_w = cur_w; memcpy(m->best, m->cur, sizeof(int) * (size_t)m->nw); }
@@ -480,6 +482,7 @@ int two_stitch_problem(const tw_batch* b, int p, const tw_params* prm, const uin
     if (win_end[i]) { /* V3:1192-1219 */
       int chosen[TW_WINDOW_CAP];
       int64_t nodes = mwis_solve(&v, window, nw, chosen);
+      if (nodes > TWO_MWIS_NODE_LIMIT) { rc = TW_ERR_MWIS_LIMIT; break; }
       if (nodes > max_nodes) max_nodes = nodes;
       for (int k = 0; k < nw; ++k) {
         int ii = ws + k;

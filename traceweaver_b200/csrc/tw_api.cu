@@ -56,7 +56,7 @@ struct tw_engine {
   int n_batches_total = 0;
   int32_t* term_ep = nullptr;
   int32_t* ep_prob = nullptr;
-  long long node_limit = 200000000LL;
+  long long node_limit = 2000000LL;   // exact MWIS search nodes per window before TW_ERR_MWIS_LIMIT
   // refit scratch (allocated on first tw_gmm_refit after bind)
   static constexpr int kStreamLen = 16384;
   int32_t* gmm_max_n = nullptr;
