@@ -265,3 +265,17 @@ extern "C" int twe_stitch_problem(const tw_batch* b, int p, const tw_params* prm
   delete wb;
   return TW_OK;
 }
+
+// exact matching of one E = 1 window given as candidate lists (unit test against scipy)
+extern "C" int twe_assign_window(int nw, const int* cnt, const double* score, const int* span, int* chosen) {
+  WindowBuf* wb = new WindowBuf;
+  int member[TW_WINDOW_CAP];
+  for (int k = 0; k < nw; ++k) {
+    wb->cnt[k] = cnt[k];
+    member[k] = k;
+    for (int r = 0; r < cnt[k]; ++r) { wb->score[k][r] = score[k * TW_K + r]; wb->idx[k][r][0] = span[k * TW_K + r]; }
+  }
+  assignment_solve(*wb, member, nw, chosen);
+  delete wb;
+  return 0;
+}

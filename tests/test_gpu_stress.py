@@ -71,6 +71,18 @@ def test_each_pass_matches_oracle(engine, name):
         # (k_score<32,64> redo).  The stitch is not compared here: 31-in-span windows this dense
         # exhaust the exact MWIS node budget in the engine and in the oracle alike.
         assert _np(sc["used_wide"]).max() == 1
+        # E = 1: the engine solves these windows as exact bipartite matchings (Hungarian; checked
+        # against scipy in tests/test_assignment.py), so it must finish within its budgets and
+        # return a conflict-free assignment
+        st = eng.stitch(prm, sc["cut"], undeleted=sc)
+        eng.status()
+        a = _np(st["assign"])
+        for pidx in range(hb.n_problems):
+            to, n = int(hb.prob_tuple_off[pidx]), int(hb.prob_in_off[pidx + 1] - hb.prob_in_off[pidx])
+            col = a[to:to + n]
+            used = col[col >= 0]
+            assert len(np.unique(used)) == len(used)
+            assert (col >= 0).mean() > 0.9
         return
     o_st = ob.stitch(o_sc["cut"], gauss=g_cpu)
     for und in (None, sc):                                   # search path and adopt / run paths

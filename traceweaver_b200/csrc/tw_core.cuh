@@ -583,6 +583,85 @@ TW_HD uint32_t window_adjacency(const WindowBuf& wb, int E, int nw, int k) {
   return m;
 }
 
+// E == 1: a candidate is one out span, so a connected component of the window is a maximum-weight
+// bipartite matching (in-spans x out spans, at most one edge per candidate, an in-span may stay
+// unmatched at weight 0).  Solved exactly in polynomial time by the Hungarian method (shortest
+// augmenting paths with potentials, sparse rows: <= 5 candidates + one private "unassigned"
+// column per in-span) instead of branch and bound, whose search explodes when ~30 in-spans compete
+// for interchangeable spans.  Same optimum as the MWIS formulation of V3:1252-1274.
+#define TW_ASSIGN_MAX_COLS (TW_WINDOW_CAP * (TW_K + 1) + 1)
+TW_HD_NOINLINE inline void assignment_solve(const WindowBuf& wb, const int* member, int m, int* best) {
+  // columns 1..ncol: distinct out spans; ncol+1..ncol+m: "row l stays unassigned"
+  int colid[TW_WINDOW_CAP * TW_K];
+  int ncol = 0;
+  short ecol[TW_WINDOW_CAP][TW_K];
+  for (int l = 0; l < m; ++l) {
+    const int k = member[l];
+    for (int r = 0; r < TW_K; ++r) {
+      ecol[l][r] = -1;
+      if (r >= wb.cnt[k] || !(TW_WEIGHT_OFFSET + wb.score[k][r] > 0.0)) continue;
+      const int span = wb.idx[k][r][0];
+      int j = 0;
+      while (j < ncol && colid[j] != span) ++j;
+      if (j == ncol) colid[ncol++] = span;
+      ecol[l][r] = (short)(j + 1);
+    }
+  }
+  const int M = ncol + m;
+  double u[TW_WINDOW_CAP + 1], vv[TW_ASSIGN_MAX_COLS], minv[TW_ASSIGN_MAX_COLS];
+  short p[TW_ASSIGN_MAX_COLS], way[TW_ASSIGN_MAX_COLS];
+  bool used[TW_ASSIGN_MAX_COLS];
+  for (int i = 0; i <= m; ++i) u[i] = 0.0;
+  for (int j = 0; j <= M; ++j) { vv[j] = 0.0; p[j] = 0; way[j] = 0; }
+  const double INF = 1e300;
+  for (int i = 1; i <= m; ++i) {
+    p[0] = (short)i;
+    int j0 = 0;
+    for (int j = 0; j <= M; ++j) { minv[j] = INF; used[j] = false; }
+    do {
+      used[j0] = true;
+      const int i0 = p[j0], l0 = i0 - 1, k0 = member[l0];
+      // relax the (sparse) row i0: its candidates cost -(10000 + score), its private column 0
+      for (int r = 0; r <= TW_K; ++r) {
+        int j;
+        double c;
+        if (r < TW_K) {
+          j = ecol[l0][r];
+          if (j < 0) continue;
+          c = -(TW_WEIGHT_OFFSET + wb.score[k0][r]);
+        } else {
+          j = ncol + i0;
+          c = 0.0;
+        }
+        if (used[j]) continue;
+        const double cur = c - u[i0] - vv[j];
+        if (cur < minv[j]) { minv[j] = cur; way[j] = (short)j0; }
+      }
+      double delta = INF;
+      int j1 = 0;
+      for (int j = 1; j <= M; ++j)
+        if (!used[j] && minv[j] < delta) { delta = minv[j]; j1 = j; }
+      for (int j = 0; j <= M; ++j) {
+        if (used[j]) { u[p[j]] += delta; vv[j] -= delta; }
+        else if (minv[j] < INF) minv[j] -= delta;
+      }
+      j0 = j1;
+    } while (p[j0] != 0);
+    do {
+      const int j1 = way[j0];
+      p[j0] = p[j1];
+      j0 = j1;
+    } while (j0);
+  }
+  for (int l = 0; l < m; ++l) best[l] = -1;
+  for (int j = 1; j <= ncol; ++j) {
+    if (p[j] == 0) continue;
+    const int l = p[j] - 1;
+    for (int r = TW_K - 1; r >= 0; --r)
+      if (ecol[l][r] == j) best[l] = r;   // (lists are sorted: the lowest rank is the heaviest edge)
+  }
+}
+
 // Solves the window; wb.adj must be filled.  Returns the number of search nodes, or -1 when
 // node_limit is exceeded (TW_ERR_MWIS_LIMIT).
 TW_HD_NOINLINE inline long long mwis_solve(WindowBuf& wb, int E, int nw, long long node_limit) {
@@ -611,6 +690,13 @@ TW_HD_NOINLINE inline long long mwis_solve(WindowBuf& wb, int E, int nw, long lo
       int k = member[0];
       if (wb.cnt[k] > 0 && TW_WEIGHT_OFFSET + wb.score[k][0] > 0.0) wb.chosen[k] = 0;
       ++nodes;
+      continue;
+    }
+    if (E == 1 && m >= 3) {   // bipartite case: exact matching in polynomial time
+      int bst[TW_WINDOW_CAP];
+      assignment_solve(wb, member, m, bst);
+      for (int l = 0; l < m; ++l) wb.chosen[member[l]] = bst[l];
+      nodes += m;
       continue;
     }
     double ub[TW_WINDOW_CAP + 1];
