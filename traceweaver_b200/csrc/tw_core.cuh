@@ -447,14 +447,15 @@ TW_HD uint8_t term_slot_eval(const ProbView& v, const ParamView& pv, int64_t in_
 
 // one combination of the candidate product space (x0-major): feasible tuple?  fills c[] / ce[]
 TW_HD bool combo_feasible(const ProbView& v, const OutWin* w, const int* lo, const int* r, const int* o_last,
-                          const uint8_t* sid, long long combo, int* c, int64_t* ce) {
+                          const uint8_t* sid, unsigned combo, int* c, int64_t* ce) {
   int x[TW_MAX_E];
   int64_t cs[TW_MAX_E];
-  long long idx = combo;
+  unsigned idx = combo;   // callers keep the product space below 2^31: 32-bit divides
   bool ok = true;
   for (int e = v.E - 1; e >= 0; --e) {
-    x[e] = (int)(idx % r[e]);
-    idx /= r[e];
+    const unsigned re = (unsigned)r[e], q = idx / re;
+    x[e] = (int)(idx - q * re);
+    idx = q;
     if (sid[o_last[e] + x[e]] == TW_SLOT_INVALID) ok = false;
   }
   if (!ok) return false;

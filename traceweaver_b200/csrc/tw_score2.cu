@@ -339,11 +339,11 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
               const int64_t gi = v.in_off + ij;
               out.topk_score[gi * TW_K + rk] = key_to_score(key);
               int32_t* ix = out.topk_idx + TW_K * (v.tuple_off + (int64_t)ij * E) + rk * E;
-              long long idx = sm.ent_combo[en];
+              unsigned idx = sm.ent_combo[en];
               for (int e = E - 1; e >= 0; --e) {
-                const int re = sm.rr[j][e];
-                ix[e] = sm.lo_abs[j][e] + (int)(idx % re);
-                idx /= re;
+                const unsigned re = (unsigned)sm.rr[j][e], q = idx / re;
+                ix[e] = sm.lo_abs[j][e] + (int)(idx - q * re);
+                idx = q;
               }
               if (stream_tid >= 0) { sm.carry_key[rk] = key; sm.carry_combo[rk] = sm.ent_combo[en]; }
             } else {
