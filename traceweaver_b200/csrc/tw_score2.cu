@@ -21,6 +21,21 @@
 
 namespace tw {
 
+// optional phase timers (build with -DTW_PROFILE_PHASES; scripts/phase_profile.py reads them)
+#ifdef TW_PROFILE_PHASES
+__device__ unsigned long long g_score2_phase[16];
+#define TW_PHASE(k)                                                                  \
+  do {                                                                               \
+    if (threadIdx.x == 0) {                                                          \
+      long long _now = clock64();                                                    \
+      atomicAdd(&g_score2_phase[k], (unsigned long long)(_now - _phase_t0));         \
+      _phase_t0 = _now;                                                              \
+    }                                                                                \
+  } while (0)
+#else
+#define TW_PHASE(k) do { } while (0)
+#endif
+
 constexpr int kStage2 = 1024;     // out spans staged per tile
 constexpr int kTbl2 = 2048;       // term-table slots per round
 constexpr int kEnt2 = 768;        // candidate combinations (= list entries) per round
@@ -66,6 +81,9 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
   Score2Smem<T>& sm = *reinterpret_cast<Score2Smem<T>*>(smem_raw);
   constexpr int W = kNarrowW;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+#ifdef TW_PROFILE_PHASES
+  long long _phase_t0 = clock64();
+#endif
   const int t = blockIdx.x;
   const int p = tiles.tile_prob[t];
   const int i0 = tiles.tile_start[t];
@@ -75,6 +93,7 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
     sm.n_ent = 0;
   }
   __syncthreads();
+  TW_PHASE(0);
   if (sm.rc != TW_OK) {
     if (tid == 0) atomicMin(err_flag, sm.rc);
     return;
@@ -153,6 +172,7 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
   for (int e = 0; e < TW_MAX_E; ++e)
     for (int wq = 0; wq < W; ++wq) sm.used[tid][e][wq] = 0u;
   __syncthreads();
+  TW_PHASE(1);
 
   // ---- per in-span: candidate ranges, table size, number of combinations
   OutWin w[TW_MAX_E];
@@ -214,6 +234,7 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
     if (ovf) sm.overflow = 1;
   }
 
+  TW_PHASE(2);
   bool pending = worker;
   while (true) {
     // ---- admit a prefix of the pending in-spans that fits the table and combination budgets
@@ -253,6 +274,7 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
     if (stream) sm.stream_tid = tid;
     if (serial) { serial_walk(); pending = false; }
     __syncthreads();
+  TW_PHASE(3);
     const int total_t = sm.total_t, total_c = sm.total_c, f_tid = sm.first_tid, l_tid = sm.last_tid;
     const int stream_tid = sm.stream_tid;
     const int chunk = stream_tid >= 0 ? kEnt2 - TW_K : 0x7fffffff;
@@ -282,6 +304,7 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
       sm.tbl[s] = val;
     }
     __syncthreads();
+  TW_PHASE(4);
     // ---- 2 + 3 per chunk of combinations (one chunk unless an in-span is being streamed)
     for (long long cbase = 0; cbase == 0 || cbase < total_c; cbase += chunk) {
       const int cend = (int)(cbase + chunk < (long long)total_c ? cbase + chunk : (long long)total_c);
@@ -318,6 +341,7 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
         sm.ent_j[slot] = (uint16_t)j;
       }
       __syncthreads();
+  TW_PHASE(5);
       // ---- 3. top-K: K rounds of segmented arg-max over the list
       const int n_ent = sm.n_ent;
       int ranks_done = 0;
@@ -357,6 +381,7 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
       }
       if (tid == 0) sm.n_carry = ranks_done;
       __syncthreads();
+  TW_PHASE(6);
       if (chunk == 0x7fffffff) break;
     }
     // ---- owners finish their in-span
@@ -380,6 +405,7 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
     if (!__syncthreads_or(pending)) break;
   }
   __syncthreads();
+  TW_PHASE(7);
 
   // ---- PerfectCut(i), V3:1034-1039, and the candidate maps for tw_stitch
   if (worker) {
@@ -406,6 +432,18 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
   }
   if (tid == 0 && sm.overflow) overflow_flag[t] = 1;
 }
+
+#ifdef TW_PROFILE_PHASES
+extern "C" int tw_debug_score2_phases(unsigned long long* out16, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out16, g_score2_phase, sizeof(unsigned long long) * 16);
+  if (e != cudaSuccess) return -2;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_score2_phase, z, sizeof z);
+  }
+  return 0;
+}
+#endif
 
 cudaError_t launch_score2(const tw_batch& b, const tw_params& prm, const tw_score_out& out, const TileList& narrow,
                           const int32_t* prev_idx, uint8_t* narrow_overflow, int* err_flag, cudaStream_t s) {
