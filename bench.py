@@ -81,7 +81,7 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.05)
 
     def __enter__(self):
         self.th.start()
