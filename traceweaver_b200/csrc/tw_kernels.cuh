@@ -14,8 +14,8 @@ constexpr int kScoreTile = kScoreThreads - 1;    // in-spans per CTA; the last t
 constexpr int kStageSpans = 1536;                // out spans staged in shared memory per tile
 constexpr int kTblCap = 3072;                    // term-table slots per CTA round (tw_core.cuh)
 constexpr int kLightCombos = 12;                 // more candidate combinations -> warp-cooperative enumeration
-constexpr int kWarpTblCap = 512;                 // term-table slots per stitch warp
-constexpr int kTakenWords = 320;                 // taken-bitmap words a stitch warp keeps in shared memory                 // term-table slots per stitch warp
+constexpr int kWarpTblCap = 192;                 // term-table slots per stitch warp (search path only)
+constexpr int kTakenWords = 256;                 // taken-bitmap words a stitch warp keeps in shared memory
 constexpr int kNarrowW = 2;                      // bitmap words per (in-span, ep): 64 candidates
 constexpr int kWideW = 64;                       // overflow kernel: 2048 candidates per ep
 constexpr int kWideThreads = 32;                 // (31 in-spans + carry-in per CTA)
