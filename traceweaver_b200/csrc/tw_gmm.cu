@@ -240,59 +240,105 @@ __device__ __forceinline__ bool params_from_stats(Fit& f, int k, int n, const do
   return ok;
 }
 
-// weighted log-probabilities of one sample (sklearn _estimate_log_gaussian_prob + log weights)
-// and their logsumexp
-template <bool FULL>
-__device__ __forceinline__ double estep(const Fit& f, int k, double x, double* a) {
-  double amax = -INFINITY;
-#pragma unroll
-  for (int c = 0; c < KC; ++c) {
-    if (c < k) {
-      double lp;
-      if (FULL) {
-        double y = dsub(dmul(x, f.pc[c]), dmul(f.mu[c], f.pc[c]));
-        lp = dmul(y, y);
-      } else {
-        double prec = dmul(f.pc[c], f.pc[c]);
-        lp = dadd(dsub(dmul(dmul(f.mu[c], f.mu[c]), prec), dmul(2.0, dmul(x, dmul(f.mu[c], prec)))),
-                  dmul(dmul(x, x), prec));
-      }
-      a[c] = dadd(dadd(dmul(-0.5, dadd(TW_LOG_2PI, lp)), f.logpc[c]), f.logw[c]);
-      amax = a[c] > amax ? a[c] : amax;
-    }
-  }
-  double s = 0.0, m = 0.0;
-#pragma unroll
-  for (int c = 0; c < KC; ++c) {
-    if (c < k) {
-      if (a[c] == amax) { m += 1.0; a[c] = 1.0; }
-      else {
-        // exp(d) < 2^-57 for d < -40: adding it to m >= 1 cannot change a double, and its effect
-        // on log1p(s) is below 1e-17 absolute — skip the (software, ~30 instruction) FP64 exp
-        const double d = a[c] - amax;
-        a[c] = d < -40.0 ? 0.0 : exp(d);
-        s += a[c];
-      }
-    }
-  }
-  if (s == 0.0 && m == 1.0) return amax;   // one component dominates: logsumexp == its log-prob
-  // a[] now holds exp(a_c - amax): responsibilities are a_c / (m + s) = exp(a_c - logsumexp),
-  // so the E-step costs one exp per component instead of two
-  const double inv = 1.0 / (m + s);
-#pragma unroll
-  for (int c = 0; c < KC; ++c)
-    if (c < k) a[c] *= inv;
-  if (m > 1.0) return log1p(s / m) + log(m) + amax;
-  return log1p(s) + amax;
+// exp(d) for d in [-40, 0], branch free (callers discard the value for d < -40): d = (64 q + j) ln2/64
+// + r, |r| <= ln2/128, exp(d) = 2^q * 2^(j/64) * P5(r).  ~1.5 ulp; ten FP64 operations, no slow
+// path, so the K per-component evaluations of one sample interleave instead of serialising behind
+// libdevice's range branches.
+__constant__ double c_exp2_64[64] = {
+    1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
+    1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
+    1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418,
+    1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
+    1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687,
+    1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783,
+    1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303,
+    1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112,
+    1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647,
+    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384,
+    1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267,
+    1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364,
+    1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062,
+    1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
+    1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
+    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
+
+__device__ __forceinline__ void load_exp_table(double* tab) {   // block-wide; call before any early return
+  if (threadIdx.x < 64) tab[threadIdx.x] = c_exp2_64[threadIdx.x];
+  __syncthreads();
 }
 
-// GaussianMixture(k, covariance_type = FULL ? 'full' : 'diag').fit(x) by one warp.
+__device__ __forceinline__ double exp_neg(const double* __restrict__ tab, double d) {
+  const double kMagic = 6755399441055744.0;                     // 1.5 * 2^52: rint() in the low word
+  const double t = fma(d, 92.33248261689366, kMagic);           // 64 / ln 2
+  const int n = __double2loint(t);
+  const double nf = t - kMagic;
+  double r = fma(nf, -0.010830424667801708, d);                 // ln2/64, high 29 bits: n * hi is exact
+  r = fma(nf, -2.8447437476627285e-11, r);
+  double p = 1.0 / 120.0;
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const double v = tab[n & 63] * p;
+  return __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
+}
+
+// E-step of one sample.  a[c] <- exp(w_c - max w) with w_c the weighted log-probabilities (sklearn
+// _estimate_log_gaussian_prob + log weights, same operation order); returns their sum t >= 1, so
+// that logsumexp = *amax + log t and the responsibilities are a[c] / t.
+template <int K, bool FULL>
+__device__ __forceinline__ double estep(const Fit& f, const double* __restrict__ tab, double x, double* a,
+                                        double* amax_out) {
+  double amax = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < K; ++c) {
+    double lp;
+    if (FULL) {
+      double y = dsub(dmul(x, f.pc[c]), dmul(f.mu[c], f.pc[c]));
+      lp = dmul(y, y);
+    } else {
+      double prec = dmul(f.pc[c], f.pc[c]);
+      lp = dadd(dsub(dmul(dmul(f.mu[c], f.mu[c]), prec), dmul(2.0, dmul(x, dmul(f.mu[c], prec)))),
+                dmul(dmul(x, x), prec));
+    }
+    a[c] = dadd(dadd(dmul(-0.5, dadd(TW_LOG_2PI, lp)), f.logpc[c]), f.logw[c]);
+    amax = a[c] > amax ? a[c] : amax;
+  }
+  double t = 0.0;
+#pragma unroll
+  for (int c = 0; c < K; ++c) {
+    // exp(d) < 2^-57 for d < -40: it cannot change a sum that holds the maximum's 1.0
+    const double d = a[c] - amax;
+    const double e = exp_neg(tab, d);
+    a[c] = d >= -40.0 ? e : 0.0;
+    t += a[c];
+  }
+  *amax_out = amax;
+  return t;
+}
+
+// running sum of logsumexp values: sum(amax) + log(prod t), the product flushed before it can overflow
+struct LogSum {
+  double acc = 0.0, prod = 1.0;
+  int cnt = 0;
+  __device__ __forceinline__ void add(double t, double amax) {
+    acc += amax;
+    prod *= t;                       // 1 <= t <= 5
+    if (++cnt == 128) { acc += log(prod); prod = 1.0; cnt = 0; }
+  }
+  __device__ __forceinline__ double total() const { return acc + log(prod); }
+};
+
+// GaussianMixture(K, covariance_type = FULL ? 'full' : 'diag').fit(x) by one warp.
 // Returns false on scikit-learn's ValueError paths; *score = mean log-likelihood under the final
 // parameters when want_score.
-template <bool FULL>
-__device__ __forceinline__ bool warp_fit(const double* __restrict__ x, int n, int k, double mean, double tol,
-                         const double* __restrict__ draws, Fit& f, bool want_score, double* score) {
+template <int K, bool FULL>
+__device__ __forceinline__ bool warp_fit(const double* __restrict__ x, int n, double mean, double tol,
+                         const double* __restrict__ draws, const double* __restrict__ tab, Fit& f,
+                         bool want_score, double* score) {
   const int lane = threadIdx.x & 31;
+  const int k = K;
   if (n < 2 || n < k) return false;
   const double shift = FULL ? mean : 0.0;
   double S0[KC], S1[KC], S2[KC], nk[KC], mup[KC];
@@ -333,50 +379,61 @@ __device__ __forceinline__ bool warp_fit(const double* __restrict__ x, int n, in
   if (!params_from_stats<FULL>(f, k, n, nk, mup, S2, shift, true)) return false;
   double lower = -INFINITY;
   for (int it = 1; it <= kEmMaxIter; ++it) {
-    double prev = lower, part = 0.0;
+    const double prev = lower;
+    LogSum ls;
 #pragma unroll
     for (int c = 0; c < KC; ++c) { S0[c] = 0.0; S1[c] = 0.0; S2[c] = 0.0; }
     for (int i = lane; i < n; i += 32) {
-      double xi = x[i], a[KC];
-      double l = estep<FULL>(f, k, xi, a);
-      part += l;
-      double xs = xi - shift;
+      double xi = x[i], a[KC], amax;
+      const double t = estep<K, FULL>(f, tab, xi, a, &amax);
+      ls.add(t, amax);
+      const double inv = 1.0 / t;
 #pragma unroll
-      for (int c = 0; c < KC; ++c)
-        if (c < k) {
-          double r = a[c];
-          S0[c] += r; S1[c] += r * xs;
-          if (!FULL) S2[c] += r * (xs * xs);
+      for (int c = 0; c < K; ++c) {
+        const double r = a[c] * inv;
+        S0[c] += r;
+        if (FULL) {
+          // deviations from the OLD mean: sum r (x - mu_new)^2 = S2 - (S1 / S0) S1 below.  Near
+          // convergence mu_new ~ mu_old, so nothing cancels, and a component of identical samples
+          // still gets cov = reg_covar (to ~1e-30) as in _estimate_gaussian_covariances_full.
+          const double dx = xi - f.mu[c];
+          const double rd = r * dx;
+          S1[c] += rd;
+          S2[c] += rd * dx;
+        } else {
+          S1[c] += r * xi;
+          S2[c] += r * (xi * xi);
         }
+      }
     }
-    lower = wsum(part) / (double)n;
+    lower = wsum(ls.total()) / (double)n;
 #pragma unroll
     for (int c = 0; c < KC; ++c) {
-      nk[c] = wsum(S0[c]) + 10.0 * kDblEps;
-      mup[c] = wsum(S1[c]) / nk[c];
-      if (!FULL) S2[c] = wsum(S2[c]);
-    }
-    if (FULL) {   // responsibilities under the OLD parameters, deviations from the NEW means
-#pragma unroll
-      for (int c = 0; c < KC; ++c) S2[c] = 0.0;
-      for (int i = lane; i < n; i += 32) {
-        double xi = x[i], a[KC];
-        (void)estep<FULL>(f, k, xi, a);
-        double xs = xi - shift;
-#pragma unroll
-        for (int c = 0; c < KC; ++c)
-          if (c < k) { double d = xs - mup[c]; S2[c] += (a[c] * d) * d; }
+      if (c < K) {
+        nk[c] = wsum(S0[c]) + 10.0 * kDblEps;
+        const double s1 = wsum(S1[c]);
+        S2[c] = wsum(S2[c]);
+        if (FULL) {
+          const double delta = s1 / nk[c];
+          S2[c] -= delta * s1;
+          if (S2[c] < 0.0) S2[c] = 0.0;
+          mup[c] = (f.mu[c] + delta) - shift;
+        } else {
+          mup[c] = s1 / nk[c];
+        }
       }
-#pragma unroll
-      for (int c = 0; c < KC; ++c) S2[c] = wsum(S2[c]);
     }
     if (!params_from_stats<FULL>(f, k, n, nk, mup, S2, shift, false)) return false;
     if (fabs(lower - prev) < kEmTol) break;
   }
   if (want_score) {
-    double part = 0.0;
-    for (int i = lane; i < n; i += 32) { double a[KC]; part += estep<FULL>(f, k, x[i], a); }
-    *score = wsum(part) / (double)n;
+    LogSum ls;
+    for (int i = lane; i < n; i += 32) {
+      double a[KC], amax;
+      const double t = estep<K, FULL>(f, tab, x[i], a, &amax);
+      ls.add(t, amax);
+    }
+    *score = wsum(ls.total()) / (double)n;
   }
   return true;
 }
@@ -482,6 +539,8 @@ k_gmm_bic(int n_terms, const int64_t* __restrict__ term_sample_off, const double
           const double* __restrict__ mean_var, const uint32_t* __restrict__ rng_skip,
           const double* __restrict__ stream, int stream_len, double* __restrict__ bic_out,
           int* __restrict__ err_flag) {
+  __shared__ double tab[64];
+  load_exp_table(tab);
   const int t = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
   if (t >= n_terms) return;
   const int lane = threadIdx.x & 31;
@@ -497,7 +556,7 @@ k_gmm_bic(int n_terms, const int64_t* __restrict__ term_sample_off, const double
       Fit f;
       double sc = 0.0;
       const double* x = delays + term_sample_off[t];
-      if (warp_fit<false>(x, n, K, mean_var[2 * t], mean_var[2 * t + 1] * kKmTol, stream + pos, f, true, &sc))
+      if (warp_fit<K, false>(x, n, mean_var[2 * t], mean_var[2 * t + 1] * kKmTol, stream + pos, tab, f, true, &sc))
         bic = -2.0 * sc * (double)n + (double)(3 * K - 1) * log((double)n);   // GaussianMixture.bic, 'diag'
     }
   }
@@ -549,6 +608,8 @@ k_gmm_final(const int32_t* __restrict__ list, const uint32_t* __restrict__ hist,
             const int32_t* __restrict__ counts, const double* __restrict__ mean_var,
             const double* __restrict__ stream100, double* __restrict__ mix_out,
             int32_t* __restrict__ n_selected_out) {
+  __shared__ double tab[64];
+  load_exp_table(tab);
   const unsigned w = (blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5;
   if (w >= hist[K]) return;
   uint32_t off = 0;
@@ -558,8 +619,8 @@ k_gmm_final(const int32_t* __restrict__ list, const uint32_t* __restrict__ hist,
   const int lane = threadIdx.x & 31;
   const int n = counts[t];
   Fit f;
-  const bool ok = warp_fit<true>(delays + term_sample_off[t], n, K, mean_var[2 * t], mean_var[2 * t + 1] * kKmTol,
-                                 stream100, f, false, nullptr);
+  const bool ok = warp_fit<K, true>(delays + term_sample_off[t], n, mean_var[2 * t], mean_var[2 * t + 1] * kKmTol,
+                                    stream100, tab, f, false, nullptr);
   if (lane == 0) {
     double* rec = mix_out + (size_t)t * TW_MIX_REC;
     for (int q = 0; q < TW_MIX_REC; ++q) rec[q] = 0.0;
