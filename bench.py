@@ -224,6 +224,7 @@ def run_ours(args):
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     h2d, d2h = solver.h2d_bytes, solver.d2h_bytes
+    chunks = len(solver._plan[1]) if solver._plan else 1
     solver.close()
 
     # ---- CPU baseline (rank 0, N=1 only): the C restatement on a bounded sample of the same services
@@ -243,7 +244,8 @@ def run_ours(args):
                          "note": "fraction of incoming spans with all children correct vs generator ground truth"},
             "e2e": {"value": total * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "traceweaver_b200.api.BatchSolver.solve(host batch) -> host arrays"},
+                    "api": "traceweaver_b200.api.BatchSolver.solve(host batch) -> host arrays",
+                    "overlap": f"{chunks} service groups round-robin on 2 streams (copies overlap kernels)"},
             "gpu_launches": int(launches),
             "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "impl": "ours",
         }

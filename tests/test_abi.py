@@ -75,3 +75,25 @@ def test_terms_follow_reference_order():
     p = Problem(in_start=s, in_end=s + 1, out_start=[s] * 3, out_end=[s] * 3, preds=[[], [0], [0, 1]])
     assert p.terms() == [(0, -1), (0, -2), (1, 0), (1, -2), (2, 1), (2, -2)]
     assert not p.is_primary(0, 2) and p.is_primary(1, 2)
+
+
+def test_batch_slice_equals_rebuilt_batch():
+    """HostBatch.slice(lo, hi) == build_batch(problems[lo:hi]) array for array (chunked solver, api.py)."""
+    from traceweaver_b200 import synth
+    from traceweaver_b200.batch import build_batch, build_batch_from_blocks
+    blocks = [synth.make_block("hotel_frontend", 3, 40, 100.0, seed=1),
+              synth.make_block("media_nginx", 4, 25, 100.0, seed=2),
+              synth.make_block("single", 2, 30, 100.0, seed=3)]
+    hb = build_batch_from_blocks(blocks)
+    probs = [blk.problem(s) for blk in blocks for s in range(blk.in_start.shape[0])]
+    full = build_batch(probs)
+    for k, v in full.arrays.items():
+        assert np.array_equal(hb.arrays[k], v), k
+    for lo, hi in ((0, 9), (0, 1), (2, 5), (3, 7), (8, 9)):
+        want = build_batch(probs[lo:hi])
+        for src in (hb, full):
+            got = src.slice(lo, hi)
+            assert got.n_problems == hi - lo
+            for k, v in want.arrays.items():
+                assert got.arrays[k].dtype == v.dtype, k
+                assert np.array_equal(got.arrays[k], v), k

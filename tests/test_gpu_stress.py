@@ -124,6 +124,26 @@ def test_whole_path_matches_oracle(name):
     assert np.array_equal(out["n_cand"], ref["n_cand_total"])
 
 
+def test_chunked_solver_matches_single_pass():
+    """BatchSolver's copy/compute overlap (service groups on two streams) must not change anything."""
+    from traceweaver_b200 import synth
+    from traceweaver_b200.api import BatchSolver
+    from traceweaver_b200.batch import build_batch_from_blocks
+    hb = build_batch_from_blocks([synth.make_block("hotel_frontend", 7, 300, 150.0, seed=5),
+                                  synth.make_block("hotel_search", 6, 200, 150.0, seed=6)])
+    one = BatchSolver(device=0, seed_select=10, chunks=1)
+    ref = {k: v.copy() for k, v in one.solve(hb).items()}
+    one.close()
+    many = BatchSolver(device=0, seed_select=10, chunks=3)
+    many.MIN_CHUNK_IN_SPANS = 0
+    for _ in range(2):                                       # second call re-uses the staging buffers
+        got = many.solve(hb)
+        for k in ref:
+            assert np.array_equal(got[k], ref[k]), k
+    assert len(many._plan[1]) == 3
+    many.close()
+
+
 def test_engine_limits_fail_loudly(engine):
     """E > 8 is rejected at bind time with TW_ERR_INVALID, not mis-solved."""
     from traceweaver_b200 import _abi

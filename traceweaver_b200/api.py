@@ -16,6 +16,7 @@ pinned memory and the results device->host; nothing is cached across calls excep
 import numpy as np
 import torch
 
+from . import _abi
 from .batch import HostBatch
 from .engine import Engine
 from .predictor import solve_bound
@@ -25,20 +26,35 @@ RESULTS = ("assign", "topk_idx", "topk_cnt", "n_cand", "counters", "mis_rank")
 
 
 class BatchSolver:
-    def __init__(self, device=0, seed_select=10):
+    """`chunks` > 1 splits the services of a batch into that many groups and runs them round-robin on
+    two CUDA streams (one engine each), so that a group's host->device and device->host copies
+    overlap another group's kernels.  The groups are independent problems: results are identical.
+    Two groups measured best on the 8192-service bench workload (scripts/time_e2e.py: 123.9 ms in one
+    piece, 113.8 in two, 117.9 in four, 131 in eight — every group pays ~3 ms of launch-latency-bound
+    kernels)."""
+
+    #: below this many in-spans a batch is solved in one piece (copies are not worth hiding)
+    MIN_CHUNK_IN_SPANS = 1 << 20
+
+    def __init__(self, device=0, seed_select=10, chunks=2):
         self.engine = Engine(device)
         self.seed_select = seed_select
+        self.chunks = max(1, int(chunks))
+        self._engines = [self.engine]
+        self._streams = None
         self._pinned_in = {}
         self._pinned_out = {}
+        self._plan = None
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
     def close(self):
-        self.engine.close()
+        for e in self._engines:
+            e.close()
 
     def _pin(self, name, a):
         """The caller's host buffer, page-locked (re-used when the same array comes back)."""
-        key = (name, a.__array_interface__["data"][0], a.nbytes)
+        key = (a.__array_interface__["data"][0], a.nbytes)
         t = self._pinned_in.get(name)
         if t is None or t[0] != key:
             src = a.view(np.int32) if a.dtype == np.uint32 else a
@@ -46,30 +62,80 @@ class BatchSolver:
             self._pinned_in[name] = t
         return t[1]
 
+    def _out_buf(self, name, n, dtype, cols=None):
+        shape = (n,) if cols is None else (n, cols)
+        buf = self._pinned_out.get(name)
+        if buf is None or tuple(buf.shape) != shape or buf.dtype != dtype:
+            buf = torch.empty(shape, dtype=dtype, pin_memory=True)
+            self._pinned_out[name] = buf
+        return buf
+
+    def _chunk_plan(self, hb: HostBatch):
+        """[(lo, hi, sub-batch)] — cached per batch object so that the pinned staging is re-used."""
+        n_in = int(hb.prob_in_off[-1])
+        C = self.chunks if n_in >= self.MIN_CHUNK_IN_SPANS else 1
+        C = min(C, hb.n_problems)
+        key = (id(hb), hb.in_start.__array_interface__["data"][0], C)
+        if self._plan is None or self._plan[0] != key:
+            if C == 1:
+                plan = [(0, hb.n_problems, hb)]
+            else:
+                # equal in-span counts per group
+                cuts = np.searchsorted(hb.prob_in_off, np.arange(1, C) * (n_in / C), side="left")
+                edges = sorted(set([0, hb.n_problems] + [int(c) for c in cuts if 0 < c < hb.n_problems]))
+                plan = [(lo, hi, hb.slice(lo, hi)) for lo, hi in zip(edges[:-1], edges[1:])]
+            self._plan = (key, plan)
+        return self._plan[1]
+
     def solve(self, hb: HostBatch, truth_assign=None, term_order=None):
-        eng = self.engine
-        dev = eng.device
-        h2d = 0
-        d = {}
-        for name, a in hb.arrays.items():
-            p = self._pin(name, a)
-            d[name] = p.to(dev, non_blocking=True)            # H2D inside the caller's timed region
-            h2d += p.numel() * p.element_size()
-        eng.bind(hb, device_arrays=d)
-        ta = None if truth_assign is None else torch.from_numpy(np.ascontiguousarray(truth_assign, np.int32)).to(dev)
-        to = None if term_order is None else torch.from_numpy(np.ascontiguousarray(term_order, np.int32)).to(dev)
-        res = solve_bound(eng, seed_select=self.seed_select, truth_assign=ta, term_order=to)
-        out = {}
-        d2h = 0
-        for name in RESULTS:
-            t = res[name]
-            buf = self._pinned_out.get(name)
-            if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
-                buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-                self._pinned_out[name] = buf
-            buf.copy_(t, non_blocking=True)                    # D2H
-            d2h += t.numel() * t.element_size()
-            out[name] = buf
-        torch.cuda.current_stream(dev).synchronize()
+        dev = self.engine.device
+        single = truth_assign is not None or term_order is not None
+        plan = [(0, hb.n_problems, hb)] if single else self._chunk_plan(hb)
+        if len(plan) > 1 and self._streams is None:
+            self._engines.append(Engine(dev.index if dev.index is not None else 0))
+            self._streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+        n_in, n_tuple = int(hb.prob_in_off[-1]), int(hb.prob_tuple_off[-1])
+        out = dict(
+            assign=self._out_buf("assign", n_tuple, torch.int32),
+            topk_idx=self._out_buf("topk_idx", _abi.TW_K * n_tuple, torch.int32),
+            topk_cnt=self._out_buf("topk_cnt", n_in, torch.uint8),
+            n_cand=self._out_buf("n_cand", n_in, torch.int32),
+            counters=self._out_buf("counters", hb.n_problems, torch.int32, 4),
+            mis_rank=self._out_buf("mis_rank", n_in, torch.int8))
+        h2d = d2h = 0
+        main = torch.cuda.current_stream(dev)
+        used = []
+        for c, (lo, hi, sub) in enumerate(plan):
+            eng = self._engines[c % len(self._engines)] if len(plan) > 1 else self.engine
+            stream = self._streams[c % 2] if len(plan) > 1 else main
+            if len(plan) > 1 and c < 2:
+                stream.wait_stream(main)
+            with torch.cuda.stream(stream):
+                d = {}
+                for name, a in sub.arrays.items():
+                    p = self._pin((c, name), a)
+                    d[name] = p.to(dev, non_blocking=True)        # H2D inside the caller's timed region
+                    h2d += p.numel() * p.element_size()
+                eng.bind(sub, device_arrays=d)
+                ta = to = None
+                if single:
+                    ta = None if truth_assign is None else torch.from_numpy(
+                        np.ascontiguousarray(truth_assign, np.int32)).to(dev)
+                    to = None if term_order is None else torch.from_numpy(
+                        np.ascontiguousarray(term_order, np.int32)).to(dev)
+                res = solve_bound(eng, seed_select=self.seed_select, truth_assign=ta, term_order=to, check=False)
+                i0, t0 = int(hb.prob_in_off[lo]), int(hb.prob_tuple_off[lo])
+                i1, t1 = int(hb.prob_in_off[hi]), int(hb.prob_tuple_off[hi])
+                for name, (b0, b1) in (("assign", (t0, t1)), ("topk_idx", (_abi.TW_K * t0, _abi.TW_K * t1)),
+                                       ("topk_cnt", (i0, i1)), ("n_cand", (i0, i1)), ("counters", (lo, hi)),
+                                       ("mis_rank", (i0, i1))):
+                    t = res[name]
+                    out[name][b0:b1].copy_(t, non_blocking=True)  # D2H
+                    d2h += t.numel() * t.element_size()
+            used.append((eng, stream))
+        for eng, stream in dict((id(e), (e, s)) for e, s in used).values():
+            with torch.cuda.stream(stream):
+                eng.status()                                      # syncs the stream, raises on engine errors
+            main.wait_stream(stream)
         self.h2d_bytes, self.d2h_bytes = h2d, d2h
         return {k: v.numpy() for k, v in out.items()}

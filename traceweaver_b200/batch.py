@@ -100,6 +100,29 @@ class HostBatch:
         ep_prob = np.repeat(np.arange(self.n_problems), np.diff(a["prob_ep_off"]))
         return bool(np.all(n_out == n_in[ep_prob]))
 
+    def slice(self, lo: int, hi: int) -> "HostBatch":
+        """Sub-batch of problems [lo, hi): offset tables rebased, span arrays are views (no copy).
+        Services are independent problems, so solving the slices separately gives the same result."""
+        a = self.arrays
+        e0, e1 = int(a["prob_ep_off"][lo]), int(a["prob_ep_off"][hi])
+        t0, t1 = int(a["ep_term_off"][e0]), int(a["ep_term_off"][e1])
+        i0, i1 = int(a["prob_in_off"][lo]), int(a["prob_in_off"][hi])
+        o0, o1 = int(a["ep_out_off"][e0]), int(a["ep_out_off"][e1])
+
+        def reb(name, x0, x1):
+            v = a[name][x0:x1 + 1]
+            return np.ascontiguousarray(v - v[0])
+
+        arrays = dict(
+            prob_in_off=reb("prob_in_off", lo, hi), prob_ep_off=reb("prob_ep_off", lo, hi),
+            prob_tuple_off=reb("prob_tuple_off", lo, hi), ep_out_off=reb("ep_out_off", e0, e1),
+            ep_term_off=reb("ep_term_off", e0, e1), ep_pred_mask=a["ep_pred_mask"][e0:e1],
+            term_src=a["term_src"][t0:t1], in_start=a["in_start"][i0:i1], in_end=a["in_end"][i0:i1],
+            out_start=a["out_start"][o0:o1], out_end=a["out_end"][o0:o1],
+            prob_gauss_off=reb("prob_gauss_off", lo, hi), term_sample_off=reb("term_sample_off", t0, t1))
+        probs = self.problems[lo:hi] if isinstance(self.problems, list) else _ProblemCount(hi - lo)
+        return HostBatch(problems=probs, arrays=arrays)
+
 
 def build_batch(problems: Sequence[Problem], validate=True) -> HostBatch:
     P = len(problems)

@@ -33,6 +33,31 @@ constexpr double kDblEps = 2.220446049250313e-16;
 constexpr int KC = TW_GMM_MAX_COMP;
 constexpr unsigned kFull = 0xffffffffu;
 
+// optional phase timers (build with -DTW_PROFILE_PHASES; scripts/phase_profile.py reads them):
+// cycles in seeding / Lloyd / initial M-step / EM / scoring, then Lloyd and EM iteration counts, fits
+#ifdef TW_PROFILE_PHASES
+__device__ unsigned long long g_gmm_phase[16];
+#define TW_GPHASE_BEGIN long long _gp_t0 = clock64()
+#define TW_GPHASE_RESET _gp_t0 = clock64()
+#define TW_GPHASE(k)                                                               \
+  do {                                                                             \
+    if ((threadIdx.x & 31) == 0) {                                                 \
+      long long _now = clock64();                                                  \
+      atomicAdd(&g_gmm_phase[k], (unsigned long long)(_now - _gp_t0));             \
+      _gp_t0 = _now;                                                               \
+    }                                                                              \
+  } while (0)
+#define TW_GCOUNT(k, v)                                                            \
+  do {                                                                             \
+    if ((threadIdx.x & 31) == 0) atomicAdd(&g_gmm_phase[k], (unsigned long long)(v)); \
+  } while (0)
+#else
+#define TW_GPHASE_BEGIN do { } while (0)
+#define TW_GPHASE_RESET do { } while (0)
+#define TW_GPHASE(k) do { } while (0)
+#define TW_GCOUNT(k, v) do { } while (0)
+#endif
+
 __device__ __forceinline__ double wsum(double v) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
@@ -70,6 +95,7 @@ __device__ __forceinline__ int nearest(const double* cen, int k, double x) {
 __device__ __forceinline__ void kmeans_label_centers(const double* __restrict__ x, int n, int k, double mean, double tol,
                                      const double* __restrict__ draws, double* cen_out) {
   const int lane = threadIdx.x & 31;
+  TW_GPHASE_BEGIN;
   double cen[KC];
 #pragma unroll
   for (int j = 0; j < KC; ++j) cen[j] = 0.0;
@@ -146,6 +172,7 @@ __device__ __forceinline__ void kmeans_label_centers(const double* __restrict__ 
     cen[ci] = cc[best];
     pot = bp;
   }
+  TW_GPHASE(0);
   // ---- Lloyd (_kmeans_single_lloyd): labels are recomputed from centres, never stored
   double prev[KC];
 #pragma unroll
@@ -204,6 +231,7 @@ __device__ __forceinline__ void kmeans_label_centers(const double* __restrict__ 
       }
     }
     have_prev = true;
+    TW_GCOUNT(5, 1);
     if (!changed) { strict = true; break; }
     if (shift_tot <= tol) break;
   }
@@ -211,6 +239,7 @@ __device__ __forceinline__ void kmeans_label_centers(const double* __restrict__ 
   // final update); otherwise sklearn re-runs the assignment with the final centres
 #pragma unroll
   for (int j = 0; j < KC; ++j) cen_out[j] = strict ? prev[j] : cen[j];
+  TW_GPHASE(1);
 }
 
 // parameters from the M-step sums.  S0 = sum r, S1 = sum r x' (x' = x - shift).
@@ -293,6 +322,10 @@ __device__ __forceinline__ double estep(const Fit& f, const double* __restrict__
   double amax = -INFINITY;
 #pragma unroll
   for (int c = 0; c < K; ++c) {
+#ifdef TW_GMM_FUSED
+    const double y = (x - f.mu[c]) * f.pc[c];
+    a[c] = fma(-0.5 * y, y, (f.logpc[c] - 0.5 * TW_LOG_2PI) + f.logw[c]);
+#else
     double lp;
     if (FULL) {
       double y = dsub(dmul(x, f.pc[c]), dmul(f.mu[c], f.pc[c]));
@@ -303,6 +336,7 @@ __device__ __forceinline__ double estep(const Fit& f, const double* __restrict__
                 dmul(dmul(x, x), prec));
     }
     a[c] = dadd(dadd(dmul(-0.5, dadd(TW_LOG_2PI, lp)), f.logpc[c]), f.logw[c]);
+#endif
     amax = a[c] > amax ? a[c] : amax;
   }
   double t = 0.0;
@@ -342,9 +376,12 @@ __device__ __forceinline__ bool warp_fit(const double* __restrict__ x, int n, do
   if (n < 2 || n < k) return false;
   const double shift = FULL ? mean : 0.0;
   double S0[KC], S1[KC], S2[KC], nk[KC], mup[KC];
+  TW_GPHASE_BEGIN;
   {
     double cen[KC];
     kmeans_label_centers(x, n, k, mean, tol, draws, cen);
+    TW_GPHASE_RESET;
+    TW_GCOUNT(7, 1);
 #pragma unroll
     for (int c = 0; c < KC; ++c) { S0[c] = 0.0; S1[c] = 0.0; S2[c] = 0.0; }
     for (int i = lane; i < n; i += 32) {
@@ -377,6 +414,7 @@ __device__ __forceinline__ bool warp_fit(const double* __restrict__ x, int n, do
     }
   }
   if (!params_from_stats<FULL>(f, k, n, nk, mup, S2, shift, true)) return false;
+  TW_GPHASE(2);
   double lower = -INFINITY;
   for (int it = 1; it <= kEmMaxIter; ++it) {
     const double prev = lower;
@@ -424,8 +462,10 @@ __device__ __forceinline__ bool warp_fit(const double* __restrict__ x, int n, do
       }
     }
     if (!params_from_stats<FULL>(f, k, n, nk, mup, S2, shift, false)) return false;
+    TW_GCOUNT(6, 1);
     if (fabs(lower - prev) < kEmTol) break;
   }
+  TW_GPHASE(3);
   if (want_score) {
     LogSum ls;
     for (int i = lane; i < n; i += 32) {
@@ -435,6 +475,7 @@ __device__ __forceinline__ bool warp_fit(const double* __restrict__ x, int n, do
     }
     *score = wsum(ls.total()) / (double)n;
   }
+  TW_GPHASE(4);
   return true;
 }
 
@@ -532,8 +573,11 @@ __global__ void k_gmm_draws(int n_problems, const int32_t* __restrict__ prob_ep_
 // and component loop of warp_fit folds away, registers hold exactly K components, and all warps of
 // an SM run the same (small) loop bodies, which keeps them in the instruction cache — the
 // single generic kernel of round 1 lost half its issue slots to instruction fetch (stall_no_inst).
+#ifndef TW_GMM_MINB
+#define TW_GMM_MINB 1
+#endif
 template <int K>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, TW_GMM_MINB)
 k_gmm_bic(int n_terms, const int64_t* __restrict__ term_sample_off, const double* __restrict__ delays,
           const int32_t* __restrict__ counts, const int32_t* __restrict__ max_n,
           const double* __restrict__ mean_var, const uint32_t* __restrict__ rng_skip,
@@ -602,7 +646,7 @@ __global__ void k_gmm_group(int n_terms, const int32_t* __restrict__ best_k, con
 
 // final 'full' fit of the terms whose BIC arg-min is K: dense warps over the grouped list
 template <int K>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, TW_GMM_MINB)
 k_gmm_final(const int32_t* __restrict__ list, const uint32_t* __restrict__ hist,
             const int64_t* __restrict__ term_sample_off, const double* __restrict__ delays,
             const int32_t* __restrict__ counts, const double* __restrict__ mean_var,
@@ -640,6 +684,18 @@ k_gmm_final(const int32_t* __restrict__ list, const uint32_t* __restrict__ hist,
     if (n_selected_out) n_selected_out[t] = ok ? K : 0;
   }
 }
+
+#ifdef TW_PROFILE_PHASES
+extern "C" int tw_debug_gmm_phases(unsigned long long* out16, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out16, g_gmm_phase, sizeof(unsigned long long) * 16);
+  if (e != cudaSuccess) return -2;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_gmm_phase, z, sizeof z);
+  }
+  return 0;
+}
+#endif
 
 cudaError_t launch_gmm_prep(int n_terms, const int64_t* term_sample_off, const double* delays,
                             const int32_t* counts, int32_t* max_n, double* mean_var, cudaStream_t s) {

@@ -29,8 +29,9 @@ def solve_batch(eng: Engine, hb, seed_select=10, truth_assign=None, term_order=N
     return solve_bound(eng, seed_select, truth_assign, term_order)
 
 
-def solve_bound(eng: Engine, seed_select=10, truth_assign=None, term_order=None):
-    """Both passes over the batch currently bound to `eng` (inputs resident in HBM)."""
+def solve_bound(eng: Engine, seed_select=10, truth_assign=None, term_order=None, check=True):
+    """Both passes over the batch currently bound to `eng` (inputs resident in HBM).  check=False
+    leaves the one host sync (engine status) to the caller, who must call eng.status()."""
     eng.prepare()                                 # prev-index scan, sorted end times
     p0 = eng.params_pass0()                       # ComputeEpPairDistParams3, every 100-span batch
     # CreateWindows2 (perfect-cut flags) + FindTopKAssignments on the undeleted lists, pass-0 params
@@ -48,7 +49,8 @@ def solve_bound(eng: Engine, seed_select=10, truth_assign=None, term_order=None)
     top = eng.score(p1, out=dict(used_lo=sc["used_lo"], used_bits=sc["used_bits"], used_wide=sc["used_wide"]))
     r1 = eng.stitch(p1, sc["cut"], undeleted=top)  # iteration 1
     n_cand = r0["n_cand"] + r1["n_cand"]          # per_span_candidates accumulates over iterations
-    eng.status()
+    if check:
+        eng.status()
     return dict(assign=r1["assign"], mis_rank=r1["mis_rank"], counters=r1["counters"], n_cand=n_cand,
                 topk_score=top["topk_score"], topk_idx=top["topk_idx"], topk_cnt=top["topk_cnt"],
                 cut=sc["cut"], params_pass1=p1, assign_pass0=r0["assign"])
