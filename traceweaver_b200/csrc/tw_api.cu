@@ -63,6 +63,7 @@ struct tw_engine {
   double* gmm_mean_var = nullptr;
   uint32_t* gmm_skip = nullptr;
   double* gmm_bic = nullptr;
+  double* gmm_cen = nullptr;      // k-means centres handed from the seeding to the Lloyd to the EM kernels
   double* gmm_stream = nullptr;
   double* gmm_stream100 = nullptr;
   uint32_t gmm_seed = 0;
@@ -361,6 +362,7 @@ static int gmm_prepare(tw_engine* eng, uint32_t seed_select, cudaStream_t s) {
   CU(eng->alloc(&eng->gmm_mean_var, (size_t)nt * 2));
   CU(eng->alloc(&eng->gmm_skip, (size_t)nt + 64));   // + histogram / cursors of the final-fit grouping
   CU(eng->alloc(&eng->gmm_bic, (size_t)nt * TW_GMM_MAX_COMP));
+  CU(eng->alloc(&eng->gmm_cen, (size_t)nt * TW_GMM_MAX_COMP));
   CU(eng->alloc(&eng->gmm_stream, (size_t)tw_engine::kStreamLen));
   CU(eng->alloc(&eng->gmm_stream100, 16));
   if (!eng->gmm_stream100_valid) {
@@ -395,9 +397,9 @@ int tw_gmm_refit(tw_engine* eng, const int64_t* term_sample_off, const double* d
   CU(launch_gmm_skip(eng->dev.n_problems, eng->dev.prob_ep_off, eng->dev.ep_term_off, term_order, eng->gmm_max_n,
                      prob_base_skip, eng->gmm_skip, s));
   CU(launch_gmm_fit(nt, term_sample_off, delays, counts, eng->gmm_max_n, eng->gmm_mean_var, eng->gmm_skip,
-                    eng->gmm_stream, tw_engine::kStreamLen, eng->gmm_stream100, eng->gmm_bic, mix_out,
-                    n_selected_out, eng->err_flag, s));
-  eng->launches += 14;   // prep, skip, 5 x bic, select, group, 5 x final
+                    eng->gmm_stream, tw_engine::kStreamLen, eng->gmm_stream100, eng->gmm_bic, eng->gmm_cen,
+                    mix_out, n_selected_out, eng->err_flag, s));
+  eng->launches += 34;   // prep, skip, 5 x (seed, lloyd, bic), select, group, 5 x (seed, lloyd, final)
   return TW_OK;
 }
 

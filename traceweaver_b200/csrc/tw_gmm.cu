@@ -78,25 +78,53 @@ struct Fit {
   double mu[KC], pc[KC], logpc[KC], logw[KC];
 };
 
-__device__ __forceinline__ int nearest(const double* cen, int k, double x) {
-  int lab = 0;
-  double best = dadd(dmul(cen[0], cen[0]), dmul(-2.0, dmul(x, cen[0])));
+// arg-min over centres of c^2 - 2 x c (the x^2 term is common), first minimum wins — evaluated as a
+// tree (depth 3 for K = 5) instead of a chain; strict "<" with the lower index on the left keeps
+// NumPy's tie rule.
+struct Near { double d; int j; };
+__device__ __forceinline__ Near near_min(Near a, Near b) { return b.d < a.d ? b : a; }
+template <int K>
+__device__ __forceinline__ int nearest(const double* cen, double x) {
+  Near v[KC];
 #pragma unroll
-  for (int j = 1; j < KC; ++j)
-    if (j < k) {
-      double d = dadd(dmul(cen[j], cen[j]), dmul(-2.0, dmul(x, cen[j])));
-      if (d < best) { best = d; lab = j; }
-    }
-  return lab;
+  for (int j = 0; j < KC; ++j) {
+    v[j].j = j;
+    v[j].d = j < K ? dadd(dmul(cen[j], cen[j]), dmul(-2.0, dmul(x, cen[j]))) : 0.0;
+  }
+  if (K == 1) return 0;
+  if (K == 2) return near_min(v[0], v[1]).j;
+  if (K == 3) return near_min(near_min(v[0], v[1]), v[2]).j;
+  if (K == 4) return near_min(near_min(v[0], v[1]), near_min(v[2], v[3])).j;
+  return near_min(near_min(near_min(v[0], v[1]), near_min(v[2], v[3])), v[4]).j;
+}
+
+// One lane's samples (i = lane, lane + 32, ...) two at a time, next pair loaded before the current
+// one is processed: f(x0, x1, valid1, s) with s the lane-local index of x0.  The two samples are
+// independent until the accumulators, which gives the FP64 pipe two chains to interleave; f must
+// add x0's contribution before x1's so that every lane sums in the same order as a plain loop.
+template <class F>
+__device__ __forceinline__ void sweep2(const double* __restrict__ x, int n, F&& f) {
+  int i = threadIdx.x & 31;
+  double a = i < n ? x[i] : 0.0;
+  double b = i + 32 < n ? x[i + 32] : 0.0;
+  for (int s = 0; i < n; i += 64, s += 2) {
+    const double x0 = a, x1 = b;
+    const bool v1 = i + 32 < n;
+    a = i + 64 < n ? x[i + 64] : 0.0;
+    b = i + 96 < n ? x[i + 96] : 0.0;
+    f(x0, x1, v1, s);
+  }
 }
 
 // KMeans(n_clusters=k, n_init=1).fit(X): returns the centres (on centred data) that define the
 // final labels_.  draws[] = this fit's random_sample() values.
-__device__ __forceinline__ void kmeans_label_centers(const double* __restrict__ x, int n, int k, double mean, double tol,
-                                     const double* __restrict__ draws, double* cen_out) {
+// k-means++ seeding of KMeans(n_clusters=K, n_init=1).fit(X) on centred data (x - mean).
+template <int K>
+__device__ __forceinline__ void seed_centres(const double* __restrict__ x, int n, double mean,
+                                             const double* __restrict__ draws, double* cen) {
   const int lane = threadIdx.x & 31;
+  const int k = K;
   TW_GPHASE_BEGIN;
-  double cen[KC];
 #pragma unroll
   for (int j = 0; j < KC; ++j) cen[j] = 0.0;
   // ---- k-means++ seeding.  First centre: RandomState.choice(n, p=1/n) = searchsorted(cdf, u,
@@ -173,27 +201,76 @@ __device__ __forceinline__ void kmeans_label_centers(const double* __restrict__ 
     pot = bp;
   }
   TW_GPHASE(0);
-  // ---- Lloyd (_kmeans_single_lloyd): labels are recomputed from centres, never stored
+}
+
+// Lloyd iterations from the seeded centres: cen[] in, the centres that define the final labels_ out.
+template <int K>
+__device__ __forceinline__ void lloyd_centres(const double* __restrict__ x, int n, double mean, double tol,
+                                              const double* cen_in, double* cen_out) {
+  const int lane = threadIdx.x & 31;
+  const int k = K;
+  TW_GPHASE_BEGIN;
+  double cen[KC];
+#pragma unroll
+  for (int j = 0; j < KC; ++j) cen[j] = cen_in[j];
+  // ---- Lloyd (_kmeans_single_lloyd).  The labels of the previous assignment (needed for the
+  // "no label changed" stop) live in two packed registers per lane when n <= 1024 (4 bits per
+  // sample, 32 samples per lane); longer sample lists recompute them from the previous centres.
   double prev[KC];
 #pragma unroll
   for (int j = 0; j < KC; ++j) prev[j] = cen[j];
   bool have_prev = false, strict = false;
+  const bool packed = n <= 1024;
+  unsigned long long lab_lo = 0ull, lab_hi = 0ull;
   for (int it = 0; it < kKmMaxIter; ++it) {
-    double sx[KC], cnt[KC];
+    double sx[KC];
+    int cnt_i[KC];
 #pragma unroll
-    for (int j = 0; j < KC; ++j) { sx[j] = 0.0; cnt[j] = 0.0; }
+    for (int j = 0; j < KC; ++j) { sx[j] = 0.0; cnt_i[j] = 0; }
     bool changed = !have_prev;
-    for (int i = lane; i < n; i += 32) {
-      double xi = x[i] - mean;
-      int lab = nearest(cen, k, xi);
-      if (have_prev && nearest(prev, k, xi) != lab) changed = true;
+    if (packed) {
+      sweep2(x, n, [&](double x0, double x1, bool v1, int s) {
 #pragma unroll
-      for (int j = 0; j < KC; ++j)
-        if (j == lab) { sx[j] += xi; cnt[j] += 1.0; }
+        for (int h = 0; h < 2; ++h) {
+          const double xi = (h ? x1 : x0) - mean;
+          const bool valid = h ? v1 : true;
+          const int lab = nearest<K>(cen, xi);
+          const int sl = s + h;
+          const unsigned sh = (unsigned)(sl & 15) * 4u;
+          const bool hi = sl >= 16;
+          const unsigned long long w = hi ? lab_hi : lab_lo;
+          changed |= valid && (int)((w >> sh) & 15ull) != lab;      // first sweep: forced true below
+          const unsigned long long nw = valid ? (w & ~(15ull << sh)) | ((unsigned long long)lab << sh) : w;
+          lab_lo = hi ? lab_lo : nw;
+          lab_hi = hi ? nw : lab_hi;
+#pragma unroll
+          for (int j = 0; j < K; ++j) {
+            const bool m = valid && j == lab;
+            sx[j] += m ? xi : 0.0;
+            cnt_i[j] += m ? 1 : 0;
+          }
+        }
+      });
+    } else {
+      for (int i = lane; i < n; i += 32) {
+        const double xi = x[i] - mean;
+        const int lab = nearest<K>(cen, xi);
+        if (have_prev && nearest<K>(prev, xi) != lab) changed = true;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          const bool m = j == lab;
+          sx[j] += m ? xi : 0.0;
+          cnt_i[j] += m ? 1 : 0;
+        }
+      }
     }
+    if (!have_prev) changed = true;
+    double cnt[KC];
+#pragma unroll
+    for (int j = 0; j < KC; ++j) cnt[j] = (double)__reduce_add_sync(kFull, cnt_i[j]);
     changed = __any_sync(kFull, changed);
 #pragma unroll
-    for (int j = 0; j < KC; ++j) { sx[j] = wsum(sx[j]); cnt[j] = wsum(cnt[j]); }
+    for (int j = 0; j < KC; ++j) sx[j] = wsum(sx[j]);
     // _relocate_empty_clusters_dense (rare): farthest point from its centre moves to the empty cluster
     for (int j = 0; j < k; ++j) {
       if (cnt[j] != 0.0) continue;
@@ -201,7 +278,11 @@ __device__ __forceinline__ void kmeans_label_centers(const double* __restrict__ 
       int fi = 0x7fffffff;
       for (int i = lane; i < n; i += 32) {
         double xi = x[i] - mean;
-        double d = xi - cen[nearest(cen, k, xi)];
+        const int nl = nearest<K>(cen, xi);
+        double cn = cen[0];
+#pragma unroll
+        for (int q = 1; q < KC; ++q) cn = q == nl ? cen[q] : cn;
+        double d = xi - cn;
         d *= d;
         if (d > fd) { fd = d; fi = i; }
       }
@@ -212,7 +293,7 @@ __device__ __forceinline__ void kmeans_label_centers(const double* __restrict__ 
         if (od > fd || (od == fd && oi < fi)) { fd = od; fi = oi; }
       }
       double xf = x[fi] - mean;
-      int ol = nearest(cen, k, xf);
+      int ol = nearest<K>(cen, xf);
 #pragma unroll
       for (int q = 0; q < KC; ++q) {
         if (q == ol) { sx[q] -= xf; cnt[q] -= 1.0; }
@@ -367,10 +448,10 @@ struct LogSum {
 // GaussianMixture(K, covariance_type = FULL ? 'full' : 'diag').fit(x) by one warp.
 // Returns false on scikit-learn's ValueError paths; *score = mean log-likelihood under the final
 // parameters when want_score.
+// The k-means initialisation arrives as its label centres `cen` (k_gmm_seed / k_gmm_lloyd).
 template <int K, bool FULL>
-__device__ __forceinline__ bool warp_fit(const double* __restrict__ x, int n, double mean, double tol,
-                         const double* __restrict__ draws, const double* __restrict__ tab, Fit& f,
-                         bool want_score, double* score) {
+__device__ __forceinline__ bool em_fit(const double* __restrict__ x, int n, double mean, const double* cen,
+                                       const double* __restrict__ tab, Fit& f, bool want_score, double* score) {
   const int lane = threadIdx.x & 31;
   const int k = K;
   if (n < 2 || n < k) return false;
@@ -378,20 +459,24 @@ __device__ __forceinline__ bool warp_fit(const double* __restrict__ x, int n, do
   double S0[KC], S1[KC], S2[KC], nk[KC], mup[KC];
   TW_GPHASE_BEGIN;
   {
-    double cen[KC];
-    kmeans_label_centers(x, n, k, mean, tol, draws, cen);
-    TW_GPHASE_RESET;
     TW_GCOUNT(7, 1);
 #pragma unroll
     for (int c = 0; c < KC; ++c) { S0[c] = 0.0; S1[c] = 0.0; S2[c] = 0.0; }
-    for (int i = lane; i < n; i += 32) {
-      double xi = x[i];
-      int lab = nearest(cen, k, xi - mean);
-      double xs = xi - shift;
+    sweep2(x, n, [&](double x0, double x1, bool v1, int) {
 #pragma unroll
-      for (int c = 0; c < KC; ++c)
-        if (c == lab) { S0[c] += 1.0; S1[c] += xs; S2[c] += xs * xs; }
-    }
+      for (int h = 0; h < 2; ++h) {
+        const double xi = h ? x1 : x0;
+        const int lab = (h ? v1 : true) ? nearest<K>(cen, xi - mean) : -1;
+        const double xs = xi - shift, xs2 = xs * xs;
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          const bool m = c == lab;
+          S0[c] += m ? 1.0 : 0.0;
+          S1[c] += m ? xs : 0.0;
+          S2[c] += m ? xs2 : 0.0;
+        }
+      }
+    });
 #pragma unroll
     for (int c = 0; c < KC; ++c) {
       nk[c] = wsum(S0[c]) + 10.0 * kDblEps;
@@ -401,14 +486,19 @@ __device__ __forceinline__ bool warp_fit(const double* __restrict__ x, int n, do
     if (FULL) {   // second sweep: sum of squared deviations from the new means
 #pragma unroll
       for (int c = 0; c < KC; ++c) S2[c] = 0.0;
-      for (int i = lane; i < n; i += 32) {
-        double xi = x[i];
-        int lab = nearest(cen, k, xi - mean);
-        double xs = xi - shift;
+      sweep2(x, n, [&](double x0, double x1, bool v1, int) {
 #pragma unroll
-        for (int c = 0; c < KC; ++c)
-          if (c == lab) { double d = xs - mup[c]; S2[c] += d * d; }
-      }
+        for (int h = 0; h < 2; ++h) {
+          const double xi = h ? x1 : x0;
+          const int lab = (h ? v1 : true) ? nearest<K>(cen, xi - mean) : -1;
+          const double xs = xi - shift;
+#pragma unroll
+          for (int c = 0; c < K; ++c) {
+            const double d = xs - mup[c];
+            S2[c] += c == lab ? d * d : 0.0;
+          }
+        }
+      });
 #pragma unroll
       for (int c = 0; c < KC; ++c) S2[c] = wsum(S2[c]);
     }
@@ -569,42 +659,120 @@ __global__ void k_gmm_draws(int n_problems, const int32_t* __restrict__ prob_ep_
   prob_draws[p] = pos;
 }
 
-// One kernel instance per component count K: with K a compile-time constant every `c < k` test
-// and component loop of warp_fit folds away, registers hold exactly K components, and all warps of
-// an SM run the same (small) loop bodies, which keeps them in the instruction cache — the
-// single generic kernel of round 1 lost half its issue slots to instruction fetch (stall_no_inst).
+// One kernel instance per component count K and per phase of the fit (seeding / Lloyd / EM): with K
+// a compile-time constant every `c < k` test and component loop folds away and registers hold
+// exactly K components; with the phases in separate launches every warp of an SM loops over the same
+// few hundred instructions.  The fused single-kernel fit of the first versions (10 k SASS
+// instructions for K = 5, warps spread over three different hot loops) lost a third of its issue
+// slots to instruction fetch (stall_no_inst, profiles/README.md).
 #ifndef TW_GMM_MINB
 #define TW_GMM_MINB 1
 #endif
+
+// Which fit a warp works on.  Model selection (list == nullptr): warp w -> term w, active iff the
+// reference tries K components for it (K <= min(#unique, 5)), draws at the term's stream position.
+// Final fits (list != nullptr): warp w -> w-th term of the group whose BIC arg-min is K, draws from
+// the random_state=100 stream.
+struct FitSel {
+  const int32_t* list;
+  const uint32_t* hist;
+  const int32_t* max_n;
+  const uint32_t* rng_skip;
+  const double* stream;
+  int stream_len;
+  int n_terms;
+};
+
 template <int K>
-__global__ void __launch_bounds__(128, TW_GMM_MINB)
-k_gmm_bic(int n_terms, const int64_t* __restrict__ term_sample_off, const double* __restrict__ delays,
-          const int32_t* __restrict__ counts, const int32_t* __restrict__ max_n,
-          const double* __restrict__ mean_var, const uint32_t* __restrict__ rng_skip,
-          const double* __restrict__ stream, int stream_len, double* __restrict__ bic_out,
-          int* __restrict__ err_flag) {
-  __shared__ double tab[64];
-  load_exp_table(tab);
-  const int t = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
-  if (t >= n_terms) return;
-  const int lane = threadIdx.x & 31;
-  double bic = INFINITY;
-  const int n = counts[t];
-  if (K <= max_n[t]) {
-    uint32_t pos = rng_skip[t];
+__device__ __forceinline__ bool select_fit(const FitSel& sel, const int32_t* __restrict__ counts, int* t_out,
+                                           const double** draws_out, int* err_flag) {
+  const unsigned w = (blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5;
+  int t;
+  const double* draws;
+  if (sel.list) {
+    if (w >= sel.hist[K]) return false;
+    uint32_t off = 0;
+#pragma unroll
+    for (int q = 1; q < K; ++q) off += sel.hist[q];
+    t = sel.list[off + w];
+    draws = sel.stream;
+  } else {
+    if (w >= (unsigned)sel.n_terms) return false;
+    t = (int)w;
+    if (K > sel.max_n[t]) return false;
+    uint32_t pos = sel.rng_skip[t];
 #pragma unroll
     for (int q = 1; q < K; ++q) pos += (uint32_t)draws_for_k(q);
-    if ((int)pos + draws_for_k(K) > stream_len) {
-      if (lane == 0) atomicMin(err_flag, (int)TW_ERR_RANGE_LIMIT);
-    } else {
-      Fit f;
-      double sc = 0.0;
-      const double* x = delays + term_sample_off[t];
-      if (warp_fit<K, false>(x, n, mean_var[2 * t], mean_var[2 * t + 1] * kKmTol, stream + pos, tab, f, true, &sc))
-        bic = -2.0 * sc * (double)n + (double)(3 * K - 1) * log((double)n);   // GaussianMixture.bic, 'diag'
+    if ((int)pos + draws_for_k(K) > sel.stream_len) {
+      if (err_flag && (threadIdx.x & 31) == 0) atomicMin(err_flag, (int)TW_ERR_RANGE_LIMIT);
+      return false;
     }
+    draws = sel.stream + pos;
   }
-  if (lane == 0) bic_out[(size_t)t * KC + (K - 1)] = bic;
+  const int n = counts[t];
+  if (n < 2 || n < K) return false;      // scikit-learn raises: the fit is skipped (BIC stays +inf)
+  *t_out = t;
+  *draws_out = draws;
+  return true;
+}
+
+template <int K>
+__global__ void __launch_bounds__(128)
+k_gmm_seed(FitSel sel, const int64_t* __restrict__ term_sample_off, const double* __restrict__ delays,
+           const int32_t* __restrict__ counts, const double* __restrict__ mean_var, double* __restrict__ cen_out,
+           int* __restrict__ err_flag) {
+  int t;
+  const double* draws;
+  if (!select_fit<K>(sel, counts, &t, &draws, err_flag)) return;
+  double cen[KC];
+  seed_centres<K>(delays + term_sample_off[t], counts[t], mean_var[2 * t], draws, cen);
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) cen_out[(size_t)t * KC + j] = cen[j];
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(128)
+k_gmm_lloyd(FitSel sel, const int64_t* __restrict__ term_sample_off, const double* __restrict__ delays,
+            const int32_t* __restrict__ counts, const double* __restrict__ mean_var, double* __restrict__ cen_io) {
+  int t;
+  const double* draws;
+  if (!select_fit<K>(sel, counts, &t, &draws, nullptr)) return;
+  double cen[KC], out[KC];
+#pragma unroll
+  for (int j = 0; j < KC; ++j) cen[j] = j < K ? cen_io[(size_t)t * KC + j] : 0.0;
+  lloyd_centres<K>(delays + term_sample_off[t], counts[t], mean_var[2 * t], mean_var[2 * t + 1] * kKmTol, cen, out);
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) cen_io[(size_t)t * KC + j] = out[j];
+  }
+}
+
+// 'diag' fit + BIC of the terms that try K components
+template <int K>
+__global__ void __launch_bounds__(128, TW_GMM_MINB)
+k_gmm_bic(FitSel sel, const int64_t* __restrict__ term_sample_off, const double* __restrict__ delays,
+          const int32_t* __restrict__ counts, const double* __restrict__ mean_var,
+          const double* __restrict__ cen_in, double* __restrict__ bic_out) {
+  __shared__ double tab[64];
+  load_exp_table(tab);
+  const int w = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (w >= sel.n_terms) return;
+  double bic = INFINITY;
+  int t;
+  const double* draws;
+  if (select_fit<K>(sel, counts, &t, &draws, nullptr)) {
+    const int n = counts[t];
+    double cen[KC];
+#pragma unroll
+    for (int j = 0; j < KC; ++j) cen[j] = j < K ? cen_in[(size_t)t * KC + j] : 0.0;
+    Fit f;
+    double sc = 0.0;
+    if (em_fit<K, false>(delays + term_sample_off[t], n, mean_var[2 * t], cen, tab, f, true, &sc))
+      bic = -2.0 * sc * (double)n + (double)(3 * K - 1) * log((double)n);   // GaussianMixture.bic, 'diag'
+  }
+  if ((threadIdx.x & 31) == 0) bic_out[(size_t)w * KC + (K - 1)] = bic;
 }
 
 // np.argmin over the BICs of the fits that did not raise (first minimum); terms without a fit get
@@ -647,24 +815,24 @@ __global__ void k_gmm_group(int n_terms, const int32_t* __restrict__ best_k, con
 // final 'full' fit of the terms whose BIC arg-min is K: dense warps over the grouped list
 template <int K>
 __global__ void __launch_bounds__(128, TW_GMM_MINB)
-k_gmm_final(const int32_t* __restrict__ list, const uint32_t* __restrict__ hist,
-            const int64_t* __restrict__ term_sample_off, const double* __restrict__ delays,
+k_gmm_final(FitSel sel, const int64_t* __restrict__ term_sample_off, const double* __restrict__ delays,
             const int32_t* __restrict__ counts, const double* __restrict__ mean_var,
-            const double* __restrict__ stream100, double* __restrict__ mix_out,
-            int32_t* __restrict__ n_selected_out) {
+            const double* __restrict__ cen_in, double* __restrict__ mix_out, int32_t* __restrict__ n_selected_out) {
   __shared__ double tab[64];
   load_exp_table(tab);
   const unsigned w = (blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5;
-  if (w >= hist[K]) return;
+  if (w >= sel.hist[K]) return;
   uint32_t off = 0;
 #pragma unroll
-  for (int q = 1; q < K; ++q) off += hist[q];
-  const int t = list[off + w];
+  for (int q = 1; q < K; ++q) off += sel.hist[q];
+  const int t = sel.list[off + w];
   const int lane = threadIdx.x & 31;
   const int n = counts[t];
+  double cen[KC];
+#pragma unroll
+  for (int j = 0; j < KC; ++j) cen[j] = j < K ? cen_in[(size_t)t * KC + j] : 0.0;
   Fit f;
-  const bool ok = warp_fit<K, true>(delays + term_sample_off[t], n, mean_var[2 * t], mean_var[2 * t + 1] * kKmTol,
-                                    stream100, tab, f, false, nullptr);
+  const bool ok = em_fit<K, true>(delays + term_sample_off[t], n, mean_var[2 * t], cen, tab, f, false, nullptr);
   if (lane == 0) {
     double* rec = mix_out + (size_t)t * TW_MIX_REC;
     for (int q = 0; q < TW_MIX_REC; ++q) rec[q] = 0.0;
@@ -718,24 +886,30 @@ cudaError_t launch_gmm_draws(int n_problems, const int32_t* prob_ep_off, const i
 }
 
 template <int K>
-static cudaError_t launch_gmm_k(int n_terms, const int64_t* term_sample_off, const double* delays,
-                                const int32_t* counts, const int32_t* max_n, const double* mean_var,
-                                const uint32_t* rng_skip, const double* stream, int stream_len, double* bic,
-                                int* err_flag, cudaStream_t s) {
-  k_gmm_bic<K><<<(n_terms + 3) / 4, 128, 0, s>>>(n_terms, term_sample_off, delays, counts, max_n, mean_var,
-                                                 rng_skip, stream, stream_len, bic, err_flag);
+static cudaError_t launch_fit_phases(const FitSel& sel, int n_warps, const int64_t* term_sample_off,
+                                     const double* delays, const int32_t* counts, const double* mean_var,
+                                     double* cen, int* err_flag, cudaStream_t s) {
+  const int blocks = (n_warps + 3) / 4;
+  k_gmm_seed<K><<<blocks, 128, 0, s>>>(sel, term_sample_off, delays, counts, mean_var, cen, err_flag);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  k_gmm_lloyd<K><<<blocks, 128, 0, s>>>(sel, term_sample_off, delays, counts, mean_var, cen);
   return cudaGetLastError();
 }
 
 cudaError_t launch_gmm_fit(int n_terms, const int64_t* term_sample_off, const double* delays,
                            const int32_t* counts, const int32_t* max_n, const double* mean_var,
                            const uint32_t* rng_skip, const double* stream, int stream_len,
-                           const double* stream100, double* bic, double* mix_out, int32_t* n_selected_out,
-                           int* err_flag, cudaStream_t s) {
+                           const double* stream100, double* bic, double* cen, double* mix_out,
+                           int32_t* n_selected_out, int* err_flag, cudaStream_t s) {
   cudaError_t e;
+  const int blocks = (n_terms + 3) / 4;
+  const FitSel sel{nullptr, nullptr, max_n, rng_skip, stream, stream_len, n_terms};
 #define TW_BIC(K)                                                                                        \
-  e = launch_gmm_k<K>(n_terms, term_sample_off, delays, counts, max_n, mean_var, rng_skip, stream, stream_len, \
-                      bic, err_flag, s);                                                                 \
+  e = launch_fit_phases<K>(sel, n_terms, term_sample_off, delays, counts, mean_var, cen, err_flag, s);   \
+  if (e != cudaSuccess) return e;                                                                        \
+  k_gmm_bic<K><<<blocks, 128, 0, s>>>(sel, term_sample_off, delays, counts, mean_var, cen, bic);         \
+  e = cudaGetLastError();                                                                                \
   if (e != cudaSuccess) return e;
   TW_BIC(5) TW_BIC(4) TW_BIC(3) TW_BIC(2) TW_BIC(1)     // longest fits first
 #undef TW_BIC
@@ -754,9 +928,12 @@ cudaError_t launch_gmm_fit(int n_terms, const int64_t* term_sample_off, const do
   k_gmm_group<<<(n_terms + 127) / 128, 128, 0, s>>>(n_terms, best_k, hist, cursor, list);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  const FitSel fin{list, hist, nullptr, nullptr, stream100, 16, n_terms};
 #define TW_FINAL(K)                                                                                      \
-  k_gmm_final<K><<<(n_terms + 3) / 4, 128, 0, s>>>(list, hist, term_sample_off, delays, counts, mean_var, \
-                                                   stream100, mix_out, n_selected_out);                  \
+  e = launch_fit_phases<K>(fin, n_terms, term_sample_off, delays, counts, mean_var, cen, nullptr, s);    \
+  if (e != cudaSuccess) return e;                                                                        \
+  k_gmm_final<K><<<blocks, 128, 0, s>>>(fin, term_sample_off, delays, counts, mean_var, cen, mix_out,    \
+                                        n_selected_out);                                                 \
   e = cudaGetLastError();                                                                                \
   if (e != cudaSuccess) return e;
   TW_FINAL(5) TW_FINAL(4) TW_FINAL(3) TW_FINAL(2) TW_FINAL(1)

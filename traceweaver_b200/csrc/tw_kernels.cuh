@@ -63,7 +63,7 @@ cudaError_t launch_gmm_draws(int n_problems, const int32_t* prob_ep_off, const i
 cudaError_t launch_gmm_fit(int n_terms, const int64_t* term_sample_off, const double* delays,
                            const int32_t* counts, const int32_t* max_n, const double* mean_var,
                            const uint32_t* rng_skip, const double* stream, int stream_len,
-                           const double* stream100, double* bic, double* mix_out,
+                           const double* stream100, double* bic, double* cen, double* mix_out,
                            int32_t* n_selected_out, int* err_flag, cudaStream_t s);
 
 }  // namespace tw
