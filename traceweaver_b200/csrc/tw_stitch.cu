@@ -17,6 +17,23 @@
 
 namespace tw {
 
+// optional phase timers (build with -DTW_PROFILE_PHASES; scripts/stitch_phase_profile.py reads them)
+#ifdef TW_PROFILE_PHASES
+__device__ unsigned long long g_stitch_phase[16];
+#define TW_SPHASE(k)                                                                 \
+  do {                                                                               \
+    if (lane == 0) {                                                                 \
+      long long _now = clock64();                                                    \
+      atomicAdd(&g_stitch_phase[k], (unsigned long long)(_now - _sp_t0));            \
+      _sp_t0 = _now;                                                                 \
+    }                                                                                \
+  } while (0)
+#define TW_SCOUNT(k, v) do { if (lane == 0) atomicAdd(&g_stitch_phase[k], (unsigned long long)(v)); } while (0)
+#else
+#define TW_SPHASE(k) do { } while (0)
+#define TW_SCOUNT(k, v) do { } while (0)
+#endif
+
 struct StitchWarpSmem {
   ProbView v;
   WindowBuf wb;
@@ -24,7 +41,125 @@ struct StitchWarpSmem {
   uint32_t tk[kTakenWords];    // taken bitmap of the service when it fits (else global memory)
   uint32_t tmp[kTakenWords];   // scratch bitmap of the run path (always left zero)
   uint8_t sid[kWarpTblCap];
+  uint32_t cconf[32];          // small-window solver: conflict mask / weight of candidate lane 5k + r
+  double cw[32];
 };
+
+// Exact MWIS of a window of <= 6 in-spans by the whole warp.  Candidate (in-span k, rank r) lives in
+// lane 5k + r; its conflicts with the other candidates come from one __match_any_sync per tuple
+// position (AssignmentIntersect, V3:1276-1281).  Every connected component of the in-span conflict
+// graph is then enumerated exhaustively: combination index = mixed-radix number over the
+// component's in-spans, lowest in-span most significant, digit r = "take rank r", digit cnt =
+// "leave unassigned" — exactly the order in which mwis_solve's depth-first search reaches the
+// leaves, so "largest total, first in that order" is the solution the sequential branch and bound
+// returns (its bound only discards subtrees that cannot strictly improve).  Totals are summed in
+// level order like cur[] there.  Returns false (nothing decided) when a component needs the
+// sequential solver: E == 1 with >= 3 in-spans (Hungarian path) or more than kSmallSpace leaves.
+constexpr int kSmallWindow = 6;
+constexpr int kSmallSpace = 4096;
+__device__ __forceinline__ bool stitch_small_window(StitchWarpSmem& sm, int E, int nw, int lane, long long* nodes_out) {
+  WindowBuf& wb = sm.wb;
+  const unsigned kAll = 0xffffffffu;
+  const int k = lane / TW_K, r = lane - TW_K * k;
+  const bool valid = k < nw && r < wb.cnt[k];
+  const unsigned vmask = __ballot_sync(kAll, valid);
+  uint32_t conf = 0u;
+  if (valid) {
+    for (int e = 0; e < E; ++e) conf |= __match_any_sync(vmask, wb.idx[k][r][e]);
+    conf &= ~(0x1fu << (TW_K * k));
+  }
+  sm.cconf[lane] = conf;
+  sm.cw[lane] = valid ? TW_WEIGHT_OFFSET + wb.score[k][r] : 0.0;
+  uint32_t am = 0u;
+#pragma unroll
+  for (int a = 0; a < kSmallWindow; ++a)
+    if ((conf >> (TW_K * a)) & 0x1fu) am |= 1u << a;
+  if (lane < nw) { wb.adj[lane] = 0u; wb.chosen[lane] = -1; }
+  __syncwarp();
+  if (am) atomicOr(&wb.adj[k], am);
+  __syncwarp();
+  int cnt[kSmallWindow];
+  uint32_t adj[kSmallWindow];
+#pragma unroll
+  for (int a = 0; a < kSmallWindow; ++a) { cnt[a] = a < nw ? wb.cnt[a] : 0; adj[a] = a < nw ? wb.adj[a] : 0u; }
+  long long nodes = 0;
+  uint32_t todo = (1u << nw) - 1u;
+  while (todo) {
+    const int seed = __ffs(todo) - 1;
+    uint32_t comp = 1u << seed, frontier = comp;
+    while (frontier) {
+      const int q = __ffs(frontier) - 1;
+      frontier &= frontier - 1u;
+      uint32_t nb = 0u;
+#pragma unroll
+      for (int a = 0; a < kSmallWindow; ++a) nb = a == q ? adj[a] : nb;
+      nb &= ~comp;
+      comp |= nb;
+      frontier |= nb;
+    }
+    todo &= ~comp;
+    const int m = __popc(comp);
+    if (m == 1) {   // isolated in-span: its best candidate, if the weight is positive
+      if (lane == 0 && wb.cnt[seed] > 0 && sm.cw[TW_K * seed] > 0.0) wb.chosen[seed] = 0;
+      ++nodes;
+      continue;
+    }
+    if (E == 1 && m >= 3) return false;
+    // radix (cnt + 1) for the in-spans of the component, 1 for the others; stride of in-span a =
+    // product of the radices after it
+    int stride[kSmallWindow];
+    int space = 1;
+#pragma unroll
+    for (int a = kSmallWindow - 1; a >= 0; --a) {
+      stride[a] = space;
+      if ((comp >> a) & 1u) space *= cnt[a] + 1;
+    }
+    if (space > kSmallSpace) return false;
+    double best_w = -1.0;
+    int best_idx = 0x7fffffff;
+    for (int idx = lane; idx < space; idx += 32) {
+      int rem = idx;
+      uint32_t sel = 0u;
+      double tot = 0.0;
+      bool ok = true;
+#pragma unroll
+      for (int a = 0; a < kSmallWindow; ++a) {
+        if ((comp >> a) & 1u) {
+          const int d = rem / stride[a];
+          rem -= d * stride[a];
+          if (d < cnt[a]) {
+            const int c = TW_K * a + d;
+            const double wgt = sm.cw[c];
+            if (!(wgt > 0.0) || (sm.cconf[c] & sel)) ok = false;
+            sel |= 1u << c;
+            tot = tot + wgt;
+          }
+        }
+      }
+      if (ok && tot > best_w) { best_w = tot; best_idx = idx; }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const double ow = __shfl_xor_sync(kAll, best_w, d);
+      const int oi = __shfl_xor_sync(kAll, best_idx, d);
+      if (ow > best_w || (ow == best_w && oi < best_idx)) { best_w = ow; best_idx = oi; }
+    }
+    {
+      int rem = best_idx;
+#pragma unroll
+      for (int a = 0; a < kSmallWindow; ++a) {
+        if ((comp >> a) & 1u) {
+          const int d = rem / stride[a];
+          rem -= d * stride[a];
+          if (lane == 0) wb.chosen[a] = d < cnt[a] ? d : -1;
+        }
+      }
+    }
+    nodes += space;
+  }
+  *nodes_out = nodes;
+  return true;
+}
 
 __global__ void __launch_bounds__(kStitchWarps * 32)
 k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_score_out spec, tw_pass_out out,
@@ -35,6 +170,9 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
   const int p = blockIdx.x * kStitchWarps + warp_in_block;
   if (p >= b.n_problems) return;
   StitchWarpSmem& sm = reinterpret_cast<StitchWarpSmem*>(smem_raw)[warp_in_block];
+#ifdef TW_PROFILE_PHASES
+  long long _sp_t0 = clock64();
+#endif
   int rc = TW_OK;
   if (lane == 0) rc = load_view(b, p, sm.v);
   rc = __shfl_sync(0xffffffffu, rc, 0);
@@ -83,6 +221,7 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
   int ws = 0;
   bool skip_run = false;
   const bool can_run = tk_smem && spec.used_lo != nullptr && out.topk_score == nullptr;
+  TW_SPHASE(0);                                  // setup + defaults
   while (ws < n) {
     // ---- run of consecutive ONE-in-span windows, one lane each.  Windows only interact through
     // the taken bits, so if (a) every in-span of the run passes the fast-path test against the bits
@@ -90,13 +229,14 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
     // one after the other would give every one of them its undeleted rank-0 tuple: commit them
     // together.  Anything else falls back to the window-at-a-time path below (same results).
     if (can_run && !skip_run) {
-      WindowCursor wc2 = wc, wc_ok = wc;
-      int R = 0;
-      while (R < 32 && ws + R < n) {
-        if (!wc2.ends_at(ws + R, n, cut)) break;   // window continues past this in-span
-        wc_ok = wc2;
-        ++R;
-      }
+      // a window that starts at ws + j is a single in-span iff the next in-span is a perfect cut
+      // (or it is the last one): at a window start the size cap cannot be the reason (count <= 2).
+      // After such a run the cursor's count is irrelevant: the next visit sees cut[] set and resets it.
+      const int ij = ws + lane;
+      const bool single = ij < n && (ij == n - 1 ? ij != 0 : cut[ij + 1] != 0);
+      const unsigned sm_mask = __ballot_sync(0xffffffffu, single);
+      const int R = sm_mask == 0xffffffffu ? 32 : __ffs(~sm_mask) - 1;
+      TW_SPHASE(1);                              // run extent (cut flags)
       if (R >= 1) {
         const bool act = lane < R;
         const int ir = ws + (act ? lane : 0);
@@ -131,6 +271,7 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
           }
         }
         __syncwarp();
+        TW_SPHASE(2);                            // run test
         if (all_ok) {
           int rank = -2;
           if (act) {
@@ -150,8 +291,11 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
           unassigned += __popc(__ballot_sync(0xffffffffu, act && rank < 0));
           not_best += __popc(__ballot_sync(0xffffffffu, act && rank != 0));
           __syncwarp();
-          wc = wc_ok;
+          wc.count = 1;
           ws += R;
+          TW_SPHASE(3);                          // run commit
+          TW_SCOUNT(10, 1);
+          TW_SCOUNT(11, R);
           continue;
         }
         skip_run = true;   // conflict: do this window the long way, then try runs again
@@ -160,9 +304,33 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
     skip_run = false;
     // ---- window extent (uniform across the warp)
     int we = ws;
-    while (!wc.ends_at(we, n, cut) && we < n - 1) ++we;
+    {
+      // cut[ws .. ws + 63] in registers; a window spans <= 31 in-spans and looks one ahead
+      const unsigned c0 = __ballot_sync(0xffffffffu, ws + lane < n && cut[ws + lane] != 0);
+      const unsigned c1 = __ballot_sync(0xffffffffu, ws + 32 + lane < n && cut[ws + 32 + lane] != 0);
+      const unsigned long long cm = ((unsigned long long)c1 << 32) | c0;
+      auto cutbit = [&](int q) { return (int)((cm >> (q - ws)) & 1ull); };
+      while (true) {   // WindowCursor::ends_at on the register copy
+        bool end;
+        if (we == n - 1) end = we != 0;
+        else {
+          end = false;
+          if (we != 0) {
+            if (cutbit(we)) wc.count = 0;
+            else if (wc.count == TW_MAX_WINDOW) { wc.count = 0; end = true; }
+          }
+          wc.count += 1;
+          if (cutbit(we + 1)) end = true;
+        }
+        if (end || we >= n - 1) break;
+        ++we;
+      }
+    }
     const int nw = we - ws + 1;
     if (nw > TW_WINDOW_CAP) { rc = TW_ERR_INVALID; break; }
+    TW_SPHASE(4);                                // window extent
+    TW_SCOUNT(12, 1);
+    TW_SCOUNT(13, nw);
 
     // ---- per-lane candidate ranges on the not-taken spans
     const bool active = lane < nw;
@@ -237,8 +405,13 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
         }
       }
     }
+    TW_SPHASE(5);                                // fast test + adopt
     // ---- slow path: term tables of the window in the warp's shared memory, evaluated by all lanes
     bool pending = active && !fast;
+#ifdef TW_PROFILE_PHASES
+    const int _n_slow = __popc(__ballot_sync(0xffffffffu, pending));
+    TW_SCOUNT(14, _n_slow);
+#endif
     if (__any_sync(0xffffffffu, pending))
     while (true) {
       int my = pending ? tsize : 0, incl = my;
@@ -306,17 +479,24 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
     }
     __syncwarp();
 
+    TW_SPHASE(6);                                // slow path
     // ---- stitch the window (V3:1192-1219)
     long long nodes = 1;
     if (nw == 1) {   // one in-span: its best candidate if the vertex weight is positive
       if (lane == 0) wb.chosen[0] = (wb.cnt[0] > 0 && TW_WEIGHT_OFFSET + wb.score[0][0] > 0.0) ? 0 : -1;
     } else {
-      if (lane < nw) wb.adj[lane] = window_adjacency(wb, E, nw, lane);
-      __syncwarp();
-      if (lane == 0) nodes = mwis_solve(wb, E, nw, node_limit);
-      nodes = __shfl_sync(0xffffffffu, nodes, 0);
+      bool solved = false;
+      if (nw <= kSmallWindow) solved = stitch_small_window(sm, E, nw, lane, &nodes);
+      if (!solved) {
+        __syncwarp();
+        if (lane < nw) wb.adj[lane] = window_adjacency(wb, E, nw, lane);
+        __syncwarp();
+        if (lane == 0) nodes = mwis_solve(wb, E, nw, node_limit);
+        nodes = __shfl_sync(0xffffffffu, nodes, 0);
+      }
     }
     __syncwarp();
+    TW_SPHASE(7);                                // adjacency + MWIS
     if (nodes < 0) { rc = TW_ERR_MWIS_LIMIT; break; }
     if (nodes > max_nodes) max_nodes = nodes;
     int rank = -2;
@@ -336,6 +516,7 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
     if (!tk_smem) __threadfence_block();
     __syncwarp();
     ws = we + 1;
+    TW_SPHASE(8);                                // window commit
   }
   if (lane == 0) {
     if (rc != TW_OK) atomicMin(err_flag, rc);
@@ -347,6 +528,18 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
     }
   }
 }
+
+#ifdef TW_PROFILE_PHASES
+extern "C" int tw_debug_stitch_phases(unsigned long long* out16, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out16, g_stitch_phase, sizeof(unsigned long long) * 16);
+  if (e != cudaSuccess) return -2;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_stitch_phase, z, sizeof z);
+  }
+  return 0;
+}
+#endif
 
 cudaError_t launch_stitch(const tw_batch& b, const tw_params& prm, const uint8_t* cut,
                           const tw_score_out& spec, const tw_pass_out& out, uint32_t* taken_words, size_t taken_n_words,
