@@ -36,9 +36,19 @@ __device__ unsigned long long g_score2_phase[16];
 #define TW_PHASE(k) do { } while (0)
 #endif
 
-constexpr int kStage2 = 1024;     // out spans staged per tile
-constexpr int kTbl2 = 2048;       // term-table slots per round
-constexpr int kEnt2 = 768;        // candidate combinations (= list entries) per round
+// Shared-memory budgets of a tile.  They are sized for FOUR resident CTAs per SM (<= 55 KB each;
+// the kernel needs 128 registers, which also allows four): the kernel is latency bound, and a
+// third more warps bought more than the extra rounds of the heavier tiles cost.
+#ifndef TW_S2_STAGE
+#define TW_S2_STAGE 640
+#define TW_S2_TBL 1152
+#define TW_S2_ENT 576
+#define TW_S2_PRM_TERMS 16
+#endif
+constexpr int kStage2 = TW_S2_STAGE;   // out spans staged per tile (else the tile reads global memory)
+constexpr int kTbl2 = TW_S2_TBL;       // term-table slots per round
+constexpr int kEnt2 = TW_S2_ENT;       // candidate combinations (= list entries) per round
+constexpr int kPrm2 = TW_S2_PRM_TERMS * TW_MIX_REC;   // staged likelihood parameters (doubles)
 
 template <int T>
 struct Score2Smem {
@@ -46,7 +56,7 @@ struct Score2Smem {
   OutWin win[TW_MAX_E];
   int64_t st_s[kStage2];
   int64_t st_e[kStage2];
-  double prm[TW_MAX_TERMS * TW_MIX_REC];
+  double prm[kPrm2];
   double tbl[kTbl2];
   unsigned long long ent_key[kEnt2];
   unsigned long long rbest[T];
@@ -73,8 +83,11 @@ __device__ __forceinline__ double key_to_score(unsigned long long k) {
   return __longlong_as_double((long long)u);
 }
 
+#ifndef TW_S2_MINB
+#define TW_S2_MINB 1
+#endif
 template <int T>
-__global__ void __launch_bounds__(T)
+__global__ void __launch_bounds__(T, TW_S2_MINB)
 k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int32_t* __restrict__ prev_idx,
          uint8_t* __restrict__ overflow_flag, int* __restrict__ err_flag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -158,16 +171,23 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
     }
   }
   const int batch0 = i0 / TW_PARAM_BATCH;
+  // likelihood parameters of the tile: staged when they fit, else read in place
+  const double* prm_base;
   if (prm.mode == TW_PARAMS_GAUSS_BATCHED) {
     int nrec = 3 * v.n_terms * TW_GAUSS_REC;   // a 127-span tile can touch three 100-span batches
     const int nb = (n + TW_PARAM_BATCH - 1) / TW_PARAM_BATCH;
     const double* src = prm.gauss + (prm.prob_gauss_off[p] + (int64_t)batch0 * v.n_terms) * TW_GAUSS_REC;
     const int avail = (nb - batch0) * v.n_terms * TW_GAUSS_REC;
     if (nrec > avail) nrec = avail;
-    for (int x = tid; x < nrec; x += T) sm.prm[x] = src[x];
+    prm_base = nrec <= kPrm2 ? sm.prm : src;
+    if (nrec <= kPrm2)
+      for (int x = tid; x < nrec; x += T) sm.prm[x] = src[x];
   } else {
     const double* src = prm.mix + (int64_t)v.term0 * TW_MIX_REC;
-    for (int x = tid; x < v.n_terms * TW_MIX_REC; x += T) sm.prm[x] = src[x];
+    const int nrec = v.n_terms * TW_MIX_REC;
+    prm_base = nrec <= kPrm2 ? sm.prm : src;
+    if (nrec <= kPrm2)
+      for (int x = tid; x < nrec; x += T) sm.prm[x] = src[x];
   }
   for (int e = 0; e < TW_MAX_E; ++e)
     for (int wq = 0; wq < W; ++wq) sm.used[tid][e][wq] = 0u;
@@ -212,8 +232,8 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
   auto serial_walk = [&]() {
     ParamView pv;
     pv.mode = prm.mode;
-    pv.gauss = sm.prm + (i / TW_PARAM_BATCH - batch0) * v.n_terms * TW_GAUSS_REC;
-    pv.mix = sm.prm;
+    pv.gauss = prm_base + (i / TW_PARAM_BATCH - batch0) * v.n_terms * TW_GAUSS_REC;
+    pv.mix = prm_base;
     TopK tk;
     tk.n = 0;
     int leaves = 0;
@@ -294,8 +314,8 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
       for (int e = 0; e < E; ++e) lo_rel[e] = sm.lo_abs[j][e] - sm.win[e].base;
       ParamView pv;
       pv.mode = prm.mode;
-      pv.gauss = sm.prm + (ij / TW_PARAM_BATCH - batch0) * v.n_terms * TW_GAUSS_REC;
-      pv.mix = sm.prm;
+      pv.gauss = prm_base + (ij / TW_PARAM_BATCH - batch0) * v.n_terms * TW_GAUSS_REC;
+      pv.mix = prm_base;
       const int64_t je = sm.ine[j];
       double val = 0.0;
       const uint8_t id = term_slot_eval(v, pv, sm.ins[j], je, sm.win, lo_rel, sm.rr[j], s - sm.tstart[j],
