@@ -131,10 +131,87 @@ struct ParamView {
   int mode;
   const double* gauss;
   const double* mix;
+  const double* etab = nullptr;   // device: shared-memory copy of c_exp2_64 -> branch-free mixture path
 };
+
+#ifdef __CUDACC__
+// exp(d) for d in [-40, 0], branch free (callers discard the value for d < -40): d = (64 q + j) ln2/64
+// + r, |r| <= ln2/128, exp(d) = 2^q * 2^(j/64) * P5(r).  ~1.5 ulp; ten FP64 operations and no slow
+// path, so independent evaluations interleave instead of serialising behind libdevice's range
+// branches.  `tab` is a shared-memory copy of c_exp2_64 (a divergent index would serialise in the
+// constant cache).
+static __constant__ double c_exp2_64[64] = {
+    1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
+    1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
+    1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418,
+    1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
+    1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687,
+    1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783,
+    1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303,
+    1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112,
+    1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647,
+    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384,
+    1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267,
+    1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364,
+    1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062,
+    1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
+    1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
+    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
+
+__device__ __forceinline__ void load_exp_table(double* tab) {   // block-wide; call before any early return
+  if (threadIdx.x < 64) tab[threadIdx.x] = c_exp2_64[threadIdx.x];
+  __syncthreads();
+}
+
+__device__ __forceinline__ double exp_neg(const double* __restrict__ tab, double d) {
+  const double kMagic = 6755399441055744.0;                     // 1.5 * 2^52: rint() in the low word
+  const double t = fma(d, 92.33248261689366, kMagic);           // 64 / ln 2
+  const int n = __double2loint(t);
+  const double nf = t - kMagic;
+  double r = fma(nf, -0.010830424667801708, d);                 // ln2/64, high 29 bits: n * hi is exact
+  r = fma(nf, -2.8447437476627285e-11, r);
+  double p = 1.0 / 120.0;
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const double v = tab[n & 63] * p;
+  return __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
+}
+
+// mix_logpdf with every component evaluated unconditionally (records are zero beyond k) and masked,
+// the exponentials from exp_neg: logsumexp = max + log(sum exp(a_c - max)), the maximum's term
+// being exactly 1.  Same per-component operation order as mix_logpdf; the result differs from it
+// by the rounding of exp / log only (~1e-16 relative).
+__device__ __forceinline__ double mix_logpdf_tab(const double* rec, double dt, const double* __restrict__ tab) {
+  const int k = (int)rec[0];
+  if (k == 0) return gauss_logpdf(rec + 1, dt);
+  double a[TW_GMM_MAX_COMP];
+  double amax = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < TW_GMM_MAX_COMP; ++c) {
+    const double y = dsub(dmul(dt, rec[1 + c]), rec[6 + c]);
+    const double w = dadd(dadd(dmul(-0.5, dadd(TW_LOG_2PI, dmul(y, y))), rec[11 + c]), rec[16 + c]);
+    a[c] = c < k ? w : -INFINITY;
+    amax = a[c] > amax ? a[c] : amax;
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int c = 0; c < TW_GMM_MAX_COMP; ++c) {
+    const double d = a[c] - amax;
+    const double e = exp_neg(tab, d);
+    s += d >= -40.0 ? e : 0.0;      // exp(d) < 2^-57 cannot change a sum that holds the maximum's 1.0
+  }
+  return dadd(log(s), amax);
+}
+#endif
 
 TW_HD double term_logpdf(const ParamView& pv, int t, double dt) {
   if (pv.mode == TW_PARAMS_GAUSS_BATCHED) return gauss_logpdf(pv.gauss + t * TW_GAUSS_REC, dt);
+#ifdef __CUDA_ARCH__
+  if (pv.etab) return mix_logpdf_tab(pv.mix + t * TW_MIX_REC, dt, pv.etab);
+#endif
   return mix_logpdf(pv.mix + t * TW_MIX_REC, dt);
 }
 

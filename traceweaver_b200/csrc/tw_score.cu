@@ -83,6 +83,7 @@ struct ScoreSmem {
   int staged;
   int overflow;
   int rc;
+  double etab[64];
 };
 
 template <int T, int W>
@@ -95,6 +96,7 @@ k_score(tw_batch b, tw_params prm, int has_params, tw_score_out out, TileList ti
   const int tid = threadIdx.x;
   const int t = blockIdx.x;
   int i0, cnt, p;
+  if (tid < 64) sm.etab[tid] = c_exp2_64[tid];   // visible after the barrier below (load_view)
   if (redo_only) {
     // wide pass: narrow tile `blockIdx.y`-independent mapping — wide tiles subdivide narrow ones
     // tiles.tile_prob/tile_start describe WIDE tiles; overflow_flag is indexed by the narrow tile
@@ -270,6 +272,7 @@ k_score(tw_batch b, tw_params prm, int has_params, tw_score_out out, TileList ti
         pv.mode = prm.mode;
         pv.gauss = sm.prm + brel * v.n_terms * TW_GAUSS_REC;
         pv.mix = sm.prm;
+        pv.etab = sm.etab;
         TopK tk;
         tk.n = 0;
         int leaves = 0;
@@ -294,6 +297,7 @@ k_score(tw_batch b, tw_params prm, int has_params, tw_score_out out, TileList ti
           pv.mode = prm.mode;
           pv.gauss = sm.prm + (id >> 6) * v.n_terms * TW_GAUSS_REC;
           pv.mix = sm.prm;
+          pv.etab = sm.etab;
           sm.tbl[s] = term_logpdf(pv, id & 63, sm.tbl[s]);
         }
       }

@@ -76,6 +76,7 @@ struct Score2Smem {
   uint16_t ent_j[kEnt2];
   uint8_t sid[kTbl2];
   uint8_t tie[T];
+  double etab[64];
 };
 
 __device__ __forceinline__ double key_to_score(unsigned long long k) {
@@ -84,7 +85,7 @@ __device__ __forceinline__ double key_to_score(unsigned long long k) {
 }
 
 #ifndef TW_S2_MINB
-#define TW_S2_MINB 1
+#define TW_S2_MINB 4
 #endif
 template <int T>
 __global__ void __launch_bounds__(T, TW_S2_MINB)
@@ -105,7 +106,7 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
     sm.overflow = 0;
     sm.n_ent = 0;
   }
-  __syncthreads();
+  load_exp_table(sm.etab);
   TW_PHASE(0);
   if (sm.rc != TW_OK) {
     if (tid == 0) atomicMin(err_flag, sm.rc);
@@ -234,6 +235,7 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
     pv.mode = prm.mode;
     pv.gauss = prm_base + (i / TW_PARAM_BATCH - batch0) * v.n_terms * TW_GAUSS_REC;
     pv.mix = prm_base;
+    pv.etab = sm.etab;
     TopK tk;
     tk.n = 0;
     int leaves = 0;
@@ -316,6 +318,7 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
       pv.mode = prm.mode;
       pv.gauss = prm_base + (ij / TW_PARAM_BATCH - batch0) * v.n_terms * TW_GAUSS_REC;
       pv.mix = prm_base;
+      pv.etab = sm.etab;
       const int64_t je = sm.ine[j];
       double val = 0.0;
       const uint8_t id = term_slot_eval(v, pv, sm.ins[j], je, sm.win, lo_rel, sm.rr[j], s - sm.tstart[j],

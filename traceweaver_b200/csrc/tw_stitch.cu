@@ -165,6 +165,8 @@ __global__ void __launch_bounds__(kStitchWarps * 32)
 k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_score_out spec, tw_pass_out out,
          uint32_t* __restrict__ taken, long long node_limit, int* __restrict__ err_flag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double etab[64];
+  load_exp_table(etab);
   const int warp_in_block = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int p = blockIdx.x * kStitchWarps + warp_in_block;
@@ -436,6 +438,7 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
         pv.mode = prm.mode;
         pv.gauss = gauss_base ? gauss_base + (int64_t)(i / TW_PARAM_BATCH) * v.n_terms * TW_GAUSS_REC : nullptr;
         pv.mix = mix_base;
+        pv.etab = etab;
         TopK tk;
         tk.n = 0;
         int leaves = 0;
@@ -455,6 +458,7 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
           pv.mode = prm.mode;
           pv.gauss = gauss_base ? gauss_base + (int64_t)(batch0 + (id >> 6)) * v.n_terms * TW_GAUSS_REC : nullptr;
           pv.mix = mix_base;
+          pv.etab = etab;
           sm.tbl[s] = term_logpdf(pv, id & 63, sm.tbl[s]);
         }
       }
