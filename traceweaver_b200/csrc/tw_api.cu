@@ -64,6 +64,7 @@ struct tw_engine {
   uint32_t* gmm_skip = nullptr;
   double* gmm_bic = nullptr;
   double* gmm_cen = nullptr;      // k-means centres handed from the seeding to the Lloyd to the EM kernels
+  GmmFork gmm_fork;               // side streams of the five per-K fit chains
   double* gmm_stream = nullptr;
   double* gmm_stream100 = nullptr;
   uint32_t gmm_seed = 0;
@@ -125,6 +126,13 @@ int tw_engine_destroy(tw_engine* eng) {
   if (!eng) return TW_OK;
   cudaSetDevice(eng->device);
   eng->release();
+  if (eng->gmm_fork.ready) {
+    cudaEventDestroy(eng->gmm_fork.fork);
+    for (int q = 0; q < TW_GMM_MAX_COMP; ++q) {
+      cudaEventDestroy(eng->gmm_fork.join[q]);
+      cudaStreamDestroy(eng->gmm_fork.side[q]);
+    }
+  }
   delete eng;
   return TW_OK;
 }
@@ -362,7 +370,15 @@ static int gmm_prepare(tw_engine* eng, uint32_t seed_select, cudaStream_t s) {
   CU(eng->alloc(&eng->gmm_mean_var, (size_t)nt * 2));
   CU(eng->alloc(&eng->gmm_skip, (size_t)nt + 64));   // + histogram / cursors of the final-fit grouping
   CU(eng->alloc(&eng->gmm_bic, (size_t)nt * TW_GMM_MAX_COMP));
-  CU(eng->alloc(&eng->gmm_cen, (size_t)nt * TW_GMM_MAX_COMP));
+  CU(eng->alloc(&eng->gmm_cen, (size_t)nt * TW_GMM_MAX_COMP * TW_GMM_MAX_COMP));   // one slab per K
+  if (!eng->gmm_fork.ready) {
+    CU(cudaEventCreateWithFlags(&eng->gmm_fork.fork, cudaEventDisableTiming));
+    for (int q = 0; q < TW_GMM_MAX_COMP; ++q) {
+      CU(cudaStreamCreateWithFlags(&eng->gmm_fork.side[q], cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&eng->gmm_fork.join[q], cudaEventDisableTiming));
+    }
+    eng->gmm_fork.ready = true;
+  }
   CU(eng->alloc(&eng->gmm_stream, (size_t)tw_engine::kStreamLen));
   CU(eng->alloc(&eng->gmm_stream100, 16));
   if (!eng->gmm_stream100_valid) {
@@ -398,7 +414,7 @@ int tw_gmm_refit(tw_engine* eng, const int64_t* term_sample_off, const double* d
                      prob_base_skip, eng->gmm_skip, s));
   CU(launch_gmm_fit(nt, term_sample_off, delays, counts, eng->gmm_max_n, eng->gmm_mean_var, eng->gmm_skip,
                     eng->gmm_stream, tw_engine::kStreamLen, eng->gmm_stream100, eng->gmm_bic, eng->gmm_cen,
-                    mix_out, n_selected_out, eng->err_flag, s));
+                    mix_out, n_selected_out, eng->err_flag, &eng->gmm_fork, s));
   eng->launches += 34;   // prep, skip, 5 x (seed, lloyd, bic), select, group, 5 x (seed, lloyd, final)
   return TW_OK;
 }

@@ -853,22 +853,50 @@ static cudaError_t launch_fit_phases(const FitSel& sel, int n_warps, const int64
   return cudaGetLastError();
 }
 
+// fork: every side stream waits for the work queued on s so far; join: s waits for every side stream
+static cudaError_t fork_streams(GmmFork* fk, cudaStream_t s) {
+  cudaError_t e = cudaEventRecord(fk->fork, s);
+  for (int q = 0; q < TW_GMM_MAX_COMP && e == cudaSuccess; ++q) e = cudaStreamWaitEvent(fk->side[q], fk->fork, 0);
+  return e;
+}
+static cudaError_t join_streams(GmmFork* fk, cudaStream_t s) {
+  cudaError_t e = cudaSuccess;
+  for (int q = 0; q < TW_GMM_MAX_COMP && e == cudaSuccess; ++q) {
+    e = cudaEventRecord(fk->join[q], fk->side[q]);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s, fk->join[q], 0);
+  }
+  return e;
+}
+
+// `cen` holds one [n_terms x 5] slab per component count: the five fit chains (seed -> Lloyd -> EM
+// for K = 5..1) only share read-only inputs, so each runs on its own side stream; kernels of
+// different chains then overlap (the EM kernels are FP64-issue bound, the k-means kernels latency
+// bound) and the chains' tails hide behind each other.
 cudaError_t launch_gmm_fit(int n_terms, const int64_t* term_sample_off, const double* delays,
                            const int32_t* counts, const int32_t* max_n, const double* mean_var,
                            const uint32_t* rng_skip, const double* stream, int stream_len,
                            const double* stream100, double* bic, double* cen, double* mix_out,
-                           int32_t* n_selected_out, int* err_flag, cudaStream_t s) {
+                           int32_t* n_selected_out, int* err_flag, GmmFork* fk, cudaStream_t s) {
   cudaError_t e;
   const int blocks = (n_terms + 3) / 4;
+  const size_t slab = (size_t)n_terms * KC;
   const FitSel sel{nullptr, nullptr, max_n, rng_skip, stream, stream_len, n_terms};
-#define TW_BIC(K)                                                                                        \
-  e = launch_fit_phases<K>(sel, n_terms, term_sample_off, delays, counts, mean_var, cen, err_flag, s);   \
-  if (e != cudaSuccess) return e;                                                                        \
-  k_gmm_bic<K><<<blocks, 128, 0, s>>>(sel, term_sample_off, delays, counts, mean_var, cen, bic);         \
-  e = cudaGetLastError();                                                                                \
+  e = fork_streams(fk, s);
   if (e != cudaSuccess) return e;
+#define TW_BIC(K)                                                                                          \
+  {                                                                                                        \
+    cudaStream_t q = fk->side[K - 1];                                                                      \
+    double* c = cen + (K - 1) * slab;                                                                      \
+    e = launch_fit_phases<K>(sel, n_terms, term_sample_off, delays, counts, mean_var, c, err_flag, q);     \
+    if (e != cudaSuccess) return e;                                                                        \
+    k_gmm_bic<K><<<blocks, 128, 0, q>>>(sel, term_sample_off, delays, counts, mean_var, c, bic);           \
+    e = cudaGetLastError();                                                                                \
+    if (e != cudaSuccess) return e;                                                                        \
+  }
   TW_BIC(5) TW_BIC(4) TW_BIC(3) TW_BIC(2) TW_BIC(1)     // longest fits first
 #undef TW_BIC
+  e = join_streams(fk, s);
+  if (e != cudaSuccess) return e;
   // group the terms by selected K so that the final fits run with every warp busy.  Scratch:
   // rng_skip (free after the BIC fits) -> hist[0..7], cursor[8..15]; bic (free after the select
   // kernel) -> the grouped list; max_n -> best_k.
@@ -885,16 +913,22 @@ cudaError_t launch_gmm_fit(int n_terms, const int64_t* term_sample_off, const do
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const FitSel fin{list, hist, nullptr, nullptr, stream100, 16, n_terms};
-#define TW_FINAL(K)                                                                                      \
-  e = launch_fit_phases<K>(fin, n_terms, term_sample_off, delays, counts, mean_var, cen, nullptr, s);    \
-  if (e != cudaSuccess) return e;                                                                        \
-  k_gmm_final<K><<<blocks, 128, 0, s>>>(fin, term_sample_off, delays, counts, mean_var, cen, mix_out,    \
-                                        n_selected_out);                                                 \
-  e = cudaGetLastError();                                                                                \
+  e = fork_streams(fk, s);
   if (e != cudaSuccess) return e;
+#define TW_FINAL(K)                                                                                        \
+  {                                                                                                        \
+    cudaStream_t q = fk->side[K - 1];                                                                      \
+    double* c = cen + (K - 1) * slab;                                                                      \
+    e = launch_fit_phases<K>(fin, n_terms, term_sample_off, delays, counts, mean_var, c, nullptr, q);      \
+    if (e != cudaSuccess) return e;                                                                        \
+    k_gmm_final<K><<<blocks, 128, 0, q>>>(fin, term_sample_off, delays, counts, mean_var, c, mix_out,      \
+                                          n_selected_out);                                                 \
+    e = cudaGetLastError();                                                                                \
+    if (e != cudaSuccess) return e;                                                                        \
+  }
   TW_FINAL(5) TW_FINAL(4) TW_FINAL(3) TW_FINAL(2) TW_FINAL(1)
 #undef TW_FINAL
-  return cudaSuccess;
+  return join_streams(fk, s);
 }
 
 }  // namespace tw

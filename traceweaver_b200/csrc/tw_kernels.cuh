@@ -60,10 +60,16 @@ cudaError_t launch_gmm_skip(int n_problems, const int32_t* prob_ep_off, const in
                             const uint32_t* prob_base_skip, uint32_t* rng_skip, cudaStream_t s);
 cudaError_t launch_gmm_draws(int n_problems, const int32_t* prob_ep_off, const int32_t* ep_term_off,
                              const int32_t* max_n, uint32_t* prob_draws, cudaStream_t s);
+// side streams + events of the refit: the five per-K fit chains are independent and run concurrently
+struct GmmFork {
+  cudaStream_t side[TW_GMM_MAX_COMP];
+  cudaEvent_t fork, join[TW_GMM_MAX_COMP];
+  bool ready = false;
+};
 cudaError_t launch_gmm_fit(int n_terms, const int64_t* term_sample_off, const double* delays,
                            const int32_t* counts, const int32_t* max_n, const double* mean_var,
                            const uint32_t* rng_skip, const double* stream, int stream_len,
                            const double* stream100, double* bic, double* cen, double* mix_out,
-                           int32_t* n_selected_out, int* err_flag, cudaStream_t s);
+                           int32_t* n_selected_out, int* err_flag, GmmFork* fk, cudaStream_t s);
 
 }  // namespace tw

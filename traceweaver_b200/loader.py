@@ -1,0 +1,237 @@
+"""Jaeger JSON traces -> SoA problems, without `Span` objects.
+
+The reference builds a `Span` object per JSON span, walks every trace tree, deep-copies the span
+lists per service and partitions them by the service at the other end before it can call
+`TraceWeaverV3.FindAssignments` (executor.py: ParseSpansJson :342-400, ParseJsonTrace :755-793,
+ProcessTraceData :798-848, the per-service loop :1080-1140, utils.GetGroundTruth utils.py:22-32,
+FindOrder executor.py:214-285).  This module restates that data path for the plain Jaeger layout
+(`--fix 2` hotel_reservation, first span "HTTP GET /hotels"; any dataset whose spans carry
+`span.kind` client/server tags and whose traces need none of the FixSpans rewrites) and emits, per
+solved service, exactly what the engine binds:
+
+    in_start / in_end            int64 [n]      the service's server spans, sorted by (start, end)
+    out_start[e] / out_end[e]    int64 [n_e]    client spans per callee, same sort, callees in the
+                                                topological order of the invocation graph
+    preds[e]                     the DAG's in-edges (precedence constraints)
+    truth[e, i]                  index of the true child in callee e's list (accuracy only)
+    ids                          (trace id, span id) per row, to map results back
+
+Same order-defining rules as the reference, because ties in `start` are broken by list order:
+files by root start time (np.argsort, executor.py:305-309), spans of a trace in pre-order with
+children sorted by start (:826-836), partitions stable-sorted by (start, end) (:1107), the trace
+cap `cnt > 1000` (:873).  tests/test_loader.py checks the output against the goldens minted from
+the reference's own loader.
+"""
+import json
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from .batch import Problem, build_batch
+
+HOTEL_FIRST_SPAN = "HTTP GET /hotels"          # executor.py:759 (--fix 2)
+MAX_TRACES = 1000                              # executor.py:873: stop once cnt > 1000
+
+
+@dataclass
+class ServiceProblem:
+    """One solved service (`process`) of a trace directory."""
+    name: str
+    in_ep: str                       # the caller partition ("client_<op>" for the entry service)
+    out_eps_given: List[str]         # callee order as the reference hands it to FindAssignments
+    out_eps: List[str]               # topological order = ep index of the engine
+    problem: Problem
+    in_ids: List[tuple]
+    out_ids: List[List[tuple]]       # per ep (topological order)
+    truth: np.ndarray                # int32 [E, n], -1 where the trace has no such child
+    graph_edges: List[tuple] = field(default_factory=list)
+
+
+def _span_kind(span):
+    kind = None
+    for tag in span["tags"]:                     # the LAST span.kind tag wins (executor.py:351-353)
+        if tag["key"] == "span.kind":
+            kind = tag["value"]
+    return kind
+
+
+def trace_files(directory: str) -> List[str]:
+    """*.json files of the directory ordered by the start time of their root span
+    (GetAllTracesInDir / TimeOrder, executor.py:287-339, without the pickle cache)."""
+    files = [f for f in os.listdir(directory) if os.path.isfile(os.path.join(directory, f)) and f.endswith("json")]
+    full = os.path.abspath(directory)
+    files = [os.path.join(full, f) for f in files]
+    starts = []
+    for path in files:
+        with open(path, "r") as fh:
+            data = json.load(fh).get("data", [])
+        t = float("inf")
+        if data:
+            root = next((s for s in data[0].get("spans", []) if len(s.get("references", [])) == 0), None)
+            if root is not None:
+                t = float(root["startTime"])
+        starts.append(t)
+    order = np.argsort(starts)
+    return [files[i] for i in order]
+
+
+class _Rows:
+    """Growing SoA of one service's spans of one kind (server or client)."""
+
+    def __init__(self):
+        self.start, self.dur, self.tid, self.sid, self.other = [], [], [], [], []
+
+    def add(self, start, dur, tid, sid, other):
+        self.start.append(start)
+        self.dur.append(dur)
+        self.tid.append(tid)
+        self.sid.append(sid)
+        self.other.append(other)
+
+
+def load_jaeger_dir(directory: str, first_span: Optional[str] = HOTEL_FIRST_SPAN, max_traces: int = MAX_TRACES,
+                    files: Optional[Sequence[str]] = None) -> List[ServiceProblem]:
+    """All solvable services of a trace directory, in the order the reference visits them."""
+    files = list(files) if files is not None else trace_files(directory)
+    ins: Dict[str, _Rows] = {}
+    outs: Dict[str, _Rows] = {}
+    cnt = 0
+    for path in files:
+        with open(path, "r") as fh:
+            data = json.load(fh)["data"]
+        accepted = []
+        for d in data:
+            spans = d["spans"]
+            if any(s["traceID"] != spans[0]["traceID"] for s in spans):
+                raise ValueError(f"{path}: different trace ids inside one trace")       # executor.py:372-374
+            if any(len(s["references"]) == 0 for s in spans):
+                accepted.append(d)
+        if len(accepted) != 1:
+            raise ValueError(f"{path}: expected exactly one rooted trace (executor.py:790)")
+        d = accepted[0]
+        spans = d["spans"]
+        proc = {pid: p["serviceName"] for pid, p in d["processes"].items()}
+        index = {s["spanID"]: k for k, s in enumerate(spans)}
+        children: List[List[int]] = [[] for _ in spans]
+        root = None
+        for k, s in enumerate(spans):
+            if len(s["references"]) == 0:
+                root = k                                                                 # the last root wins (:822-823)
+            for ref in s["references"]:
+                children[index[ref["spanID"]]].append(k)
+        if spans[root]["operationName"] != first_span and first_span is not None:
+            continue
+        for ch in children:
+            ch.sort(key=lambda k: spans[k]["startTime"])                                  # stable (:826-829)
+        parent = [index[s["references"][0]["spanID"]] if s["references"] else -1 for s in spans]
+        stack = [root]
+        while stack:                                                                     # pre-order (:831-836)
+            k = stack.pop()
+            s = spans[k]
+            kind = _span_kind(s)
+            me = proc[s["processID"]]
+            if kind == "client":
+                if len(children[k]) != 1:
+                    raise ValueError(f"{path}: client span with {len(children[k])} children (spans.py:33)")
+                other = proc[spans[children[k][0]]["processID"]]                         # GetChildProcess
+                outs.setdefault(me, _Rows()).add(s["startTime"], s["duration"], s["traceID"], s["spanID"], other)
+            elif kind == "server":
+                if parent[k] < 0:
+                    other = "client_" + s["operationName"]                              # GetParentProcess, root
+                else:
+                    if len(s["references"]) != 1:
+                        raise ValueError(f"{path}: server span with several references (spans.py:41)")
+                    other = proc[spans[parent[k]]["processID"]]
+                ins.setdefault(me, _Rows()).add(s["startTime"], s["duration"], s["traceID"], s["spanID"], other)
+            else:
+                raise ValueError(f"{path}: span.kind {kind!r} (executor.py:819)")
+            stack.extend(reversed(children[k]))
+        cnt += 1
+        if cnt > max_traces:
+            break
+
+    services = []
+    for process, o in outs.items():                                                      # executor.py:1080
+        if not o.start or process not in ins:
+            continue
+        sp = _service_problem(process, ins[process], o)
+        if sp is not None:
+            services.append(sp)
+    return services
+
+
+def _partition(rows: _Rows):
+    """PartitionSpansByEndPoint (executor.py:1100-1109): {ep: row indices sorted by (start, end)},
+    eps in first-appearance order, ties in list order."""
+    parts: Dict[str, List[int]] = {}
+    for k, ep in enumerate(rows.other):
+        parts.setdefault(ep, []).append(k)
+    start = np.asarray(rows.start, np.int64)
+    end = start + np.asarray(rows.dur, np.int64)
+    for ep, idx in parts.items():
+        a = np.asarray(idx)
+        order = np.lexsort((end[a], start[a]))       # stable, primary key start, secondary end
+        parts[ep] = a[order]
+    return parts, start, end
+
+
+def _service_problem(process, i_rows: _Rows, o_rows: _Rows) -> Optional[ServiceProblem]:
+    import networkx as nx
+    in_parts, i_start, i_end = _partition(i_rows)
+    out_parts, o_start, o_end = _partition(o_rows)
+    if len(in_parts) > 1:
+        return None                                                                      # "SKIPPING THIS PROCESS", :1121
+    in_ep, in_idx = next(iter(in_parts.items()))
+    given = list(out_parts.keys())
+    n = len(in_idx)
+    i_tid = np.asarray(i_rows.tid)[in_idx]
+    # ground truth: the first span of the partition with the in-span's trace id (utils.py:22-32)
+    truth_given = np.full((len(given), n), -1, np.int32)
+    for g, ep in enumerate(given):
+        first: Dict[str, int] = {}
+        for pos, k in enumerate(out_parts[ep]):
+            first.setdefault(o_rows.tid[k], pos)
+        truth_given[g] = [first.get(t, -1) for t in i_tid]
+    # FindOrder (executor.py:214-285): complete digraph minus every order some trace violates
+    G = nx.DiGraph()
+    for ep in given:
+        G.add_node(ep)
+    for a in given:
+        for b in given:
+            if a != b:
+                G.add_edge(a, b)
+    if (truth_given < 0).any():
+        raise ValueError(f"{process}: an in-span has no child at some callee (FindOrder would raise KeyError)")
+    ts = np.stack([o_start[out_parts[ep]][truth_given[g]] for g, ep in enumerate(given)])     # [E, n]
+    te = np.stack([o_end[out_parts[ep]][truth_given[g]] for g, ep in enumerate(given)])
+    for a in range(len(given)):
+        for b in range(len(given)):
+            if a != b and G.has_edge(given[a], given[b]) and bool((te[a] > ts[b]).any()):
+                G.remove_edge(given[a], given[b])                                        # x.end > y.start (:250, :262)
+    topo = list(nx.topological_sort(G))                                                  # traceweaver_v1.py:37-39
+    pos = {ep: e for e, ep in enumerate(topo)}
+    g_of = [given.index(ep) for ep in topo]
+    preds = [[pos[b] for b, _ in G.in_edges(ep)] for ep in topo]
+    out_idx = [out_parts[ep] for ep in topo]
+    prob = Problem(in_start=i_start[in_idx], in_end=i_end[in_idx],
+                   out_start=[o_start[ix] for ix in out_idx], out_end=[o_end[ix] for ix in out_idx],
+                   preds=preds, name=process)
+    return ServiceProblem(
+        name=process, in_ep=in_ep, out_eps_given=given, out_eps=topo, problem=prob,
+        in_ids=[(i_rows.tid[k], i_rows.sid[k]) for k in in_idx],
+        out_ids=[[(o_rows.tid[k], o_rows.sid[k]) for k in ix] for ix in out_idx],
+        truth=np.ascontiguousarray(truth_given[g_of]), graph_edges=list(G.edges()))
+
+
+def to_host_batch(services: Sequence[ServiceProblem]):
+    """One bindable batch for all services that are in the accelerated regime (n_out == n_in)."""
+    return build_batch([s.problem for s in services])
+
+
+def accuracy(service: ServiceProblem, assign: np.ndarray) -> float:
+    """utils.AccuracyForService (utils.py:34-60) on index arrays: fraction of in-spans whose child
+    is right at EVERY callee.  `assign` is the engine's [E, n] block of this service."""
+    ok = (np.asarray(assign).reshape(service.truth.shape) == service.truth).all(axis=0)
+    return float(ok.mean()) if ok.size else 0.0
