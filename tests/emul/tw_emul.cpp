@@ -279,3 +279,111 @@ extern "C" int twe_assign_window(int nw, const int* cnt, const double* score, co
   delete wb;
   return 0;
 }
+
+// one window through the sequential solver of the stitch kernel (adjacency + components + branch and
+// bound / Hungarian); returns the node count (-1 = node limit)
+extern "C" long long twe_mwis_window(int nw, int E, const int* cnt, const double* score, const int* idx,
+                                     int* chosen, long long node_limit) {
+  WindowBuf* wb = new WindowBuf;
+  for (int k = 0; k < nw; ++k) {
+    wb->cnt[k] = cnt[k];
+    for (int r = 0; r < cnt[k]; ++r) {
+      wb->score[k][r] = score[k * TW_K + r];
+      for (int e = 0; e < E; ++e) wb->idx[k][r][e] = idx[(k * TW_K + r) * E + e];
+    }
+  }
+  for (int k = 0; k < nw; ++k) wb->adj[k] = window_adjacency(*wb, E, nw, k);
+  long long nodes = mwis_solve(*wb, E, nw, node_limit);
+  for (int k = 0; k < nw; ++k) chosen[k] = wb->chosen[k];
+  delete wb;
+  return nodes;
+}
+
+// The warp-parallel solver of tw_stitch.cu (stitch_small_window) restated for one thread: candidate
+// (k, r) = "lane" 5k + r, conflict masks per candidate, components of the in-span conflict graph,
+// exhaustive mixed-radix enumeration (lowest in-span most significant, digit cnt = unassigned),
+// largest total first, then the lowest combination index.  Returns 0 when the kernel would fall back
+// to the sequential solver (E == 1 component of >= 3 in-spans, or more than `space_cap` leaves).
+extern "C" int twe_small_window(int nw, int E, const int* cnt_in, const double* score, const int* idx,
+                                int* chosen, int space_cap) {
+  const int KW = 6;
+  if (nw > KW) return 0;
+  uint32_t conf[32] = {0};
+  double cw[32] = {0};
+  auto valid = [&](int c) { int k = c / TW_K, r = c % TW_K; return k < nw && r < cnt_in[k]; };
+  for (int a = 0; a < 32; ++a) {
+    if (!valid(a)) continue;
+    cw[a] = TW_WEIGHT_OFFSET + score[a];
+    for (int b = 0; b < 32; ++b) {
+      if (!valid(b) || a / TW_K == b / TW_K) continue;
+      for (int e = 0; e < E; ++e)
+        if (idx[a * E + e] == idx[b * E + e]) conf[a] |= 1u << b;
+    }
+  }
+  uint32_t adj[KW] = {0};
+  for (int a = 0; a < 32; ++a)
+    for (int q = 0; q < KW; ++q)
+      if ((conf[a] >> (TW_K * q)) & 0x1fu) adj[a / TW_K] |= 1u << q;
+  for (int k = 0; k < nw; ++k) chosen[k] = -1;
+  uint32_t todo = (1u << nw) - 1u;
+  while (todo) {
+    int seed = 0;
+    while (!(todo >> seed & 1u)) ++seed;
+    uint32_t comp = 1u << seed, frontier = comp;
+    while (frontier) {
+      int q = 0;
+      while (!(frontier >> q & 1u)) ++q;
+      frontier &= frontier - 1u;
+      uint32_t nb = adj[q] & ~comp;
+      comp |= nb;
+      frontier |= nb;
+    }
+    todo &= ~comp;
+    int m = 0;
+    for (int a = 0; a < KW; ++a) m += (comp >> a) & 1u;
+    if (m == 1) {
+      if (cnt_in[seed] > 0 && cw[TW_K * seed] > 0.0) chosen[seed] = 0;
+      continue;
+    }
+    if (E == 1 && m >= 3) return 0;
+    int stride[KW], space = 1;
+    for (int a = KW - 1; a >= 0; --a) {
+      stride[a] = space;
+      if ((comp >> a) & 1u) space *= (a < nw ? cnt_in[a] : 0) + 1;
+    }
+    if (space > space_cap) return 0;
+    double best_w = -1.0;
+    int best_idx = 0x7fffffff;
+    for (int lane = 0; lane < 32; ++lane) {          // lanes stride over the leaves, then the warp reduces
+      double lw = -1.0;
+      int li = 0x7fffffff;
+      for (int id = lane; id < space; id += 32) {
+        int rem = id;
+        uint32_t sel = 0;
+        double tot = 0.0;
+        bool ok = true;
+        for (int a = 0; a < KW; ++a) {
+          if (!((comp >> a) & 1u)) continue;
+          int d = rem / stride[a];
+          rem -= d * stride[a];
+          if (d < cnt_in[a]) {
+            int c = TW_K * a + d;
+            if (!(cw[c] > 0.0) || (conf[c] & sel)) ok = false;
+            sel |= 1u << c;
+            tot = tot + cw[c];
+          }
+        }
+        if (ok && tot > lw) { lw = tot; li = id; }
+      }
+      if (lw > best_w || (lw == best_w && li < best_idx)) { best_w = lw; best_idx = li; }
+    }
+    int rem = best_idx;
+    for (int a = 0; a < KW; ++a) {
+      if (!((comp >> a) & 1u)) continue;
+      int d = rem / stride[a];
+      rem -= d * stride[a];
+      chosen[a] = d < cnt_in[a] ? d : -1;
+    }
+  }
+  return 1;
+}
