@@ -4,10 +4,11 @@ The reference builds a `Span` object per JSON span, walks every trace tree, deep
 lists per service and partitions them by the service at the other end before it can call
 `TraceWeaverV3.FindAssignments` (executor.py: ParseSpansJson :342-400, ParseJsonTrace :755-793,
 ProcessTraceData :798-848, the per-service loop :1080-1140, utils.GetGroundTruth utils.py:22-32,
-FindOrder executor.py:214-285).  This module restates that data path for the plain Jaeger layout
-(`--fix 2` hotel_reservation, first span "HTTP GET /hotels"; any dataset whose spans carry
-`span.kind` client/server tags and whose traces need none of the FixSpans rewrites) and emits, per
-solved service, exactly what the engine binds:
+FindOrder executor.py:214-285).  This module restates that data path for two of the reference's
+dataset layouts — "hotel": spans as recorded (`--fix 2` hotel_reservation, first span
+"HTTP GET /hotels"; any dataset whose spans carry `span.kind` client/server tags), "media": the
+FixSpans2 rewrite (`--fix 1` media_microservices, executor.py:539-640) — and emits, per solved
+service, exactly what the engine binds:
 
     in_start / in_end            int64 [n]      the service's server spans, sorted by (start, end)
     out_start[e] / out_end[e]    int64 [n_e]    client spans per callee, same sort, callees in the
@@ -20,7 +21,8 @@ Same order-defining rules as the reference, because ties in `start` are broken b
 files by root start time (np.argsort, executor.py:305-309), spans of a trace in pre-order with
 children sorted by start (:826-836), partitions stable-sorted by (start, end) (:1107), the trace
 cap `cnt > 1000` (:873).  tests/test_loader.py checks the output against the goldens minted from
-the reference's own loader.
+the reference's own loader (12 hotel + 6 media services: arrays, ids, graph, ground truth equal).
+Not built: `--fix 0/3/4/5` (nodejs FixSpans, Alibaba self-loop rewriting).
 """
 import json
 import os
@@ -32,6 +34,7 @@ import numpy as np
 from .batch import Problem, build_batch
 
 HOTEL_FIRST_SPAN = "HTTP GET /hotels"          # executor.py:759 (--fix 2)
+MEDIA_FIRST_SPAN = "ComposeReview"             # executor.py:758 (--fix 1)
 MAX_TRACES = 1000                              # executor.py:873: stop once cnt > 1000
 
 
@@ -91,9 +94,89 @@ class _Rows:
         self.other.append(other)
 
 
+def _nodes_plain(d, path):
+    """Spans of one trace as the reference holds them after ParseSpansJson (no rewrite): dict order =
+    JSON order.  node = [trace, sid, start, dur, op, service, kind, parent position or -1]."""
+    spans = d["spans"]
+    proc = {pid: p["serviceName"] for pid, p in d["processes"].items()}
+    index = {s["spanID"]: k for k, s in enumerate(spans)}
+    nodes = []
+    for s in spans:
+        if len(s["references"]) > 1:
+            raise ValueError(f"{path}: span with several references (spans.py:41)")
+        par = index[s["references"][0]["spanID"]] if s["references"] else -1
+        nodes.append([s["traceID"], s["spanID"], s["startTime"], s["duration"], s["operationName"],
+                      proc[s["processID"]], _span_kind(s), par])
+    return nodes
+
+
+def _nodes_media(d, path):
+    """FixSpans2 (executor.py:539-640), the `--fix 1` rewrite of media_microservices traces, whose
+    spans carry no span.kind: the "ComposeReview" span becomes the root (its ancestors are dropped,
+    its id becomes the trace id), spans in the same process as their parent are dropped, every
+    remaining span is a server span and gets a client twin with the same timing in its parent's
+    process.  Dict order after the rewrite: stable sort by start of [servers in JSON order with the
+    new root last, twins in the same order]."""
+    spans = d["spans"]
+    proc = {pid: p["serviceName"] for pid, p in d["processes"].items()}
+    index = {s["spanID"]: k for k, s in enumerate(spans)}
+    parent = [index[s["references"][0]["spanID"]] if s["references"] else -1 for s in spans]
+    roots = [k for k, s in enumerate(spans) if s["operationName"] == MEDIA_FIRST_SPAN]
+    if len(roots) != 1:
+        raise ValueError(f"{path}: expected one {MEDIA_FIRST_SPAN} span")
+    c = roots[0]
+    dropped = set()
+    k = parent[c]
+    while k >= 0:                                                                        # DeleteAncestors
+        dropped.add(k)
+        k = parent[k]
+    order = [k for k in range(len(spans)) if k not in dropped and k != c] + [c]
+    for k in order:                                                                      # same-process children
+        if k != c and parent[k] in dropped:
+            raise ValueError(f"{path}: span hangs off a dropped ancestor (FixSpans2 would raise KeyError)")
+    same = {k for k in order if k != c and spans[parent[k]]["processID"] == spans[k]["processID"]}
+    keep = [k for k in order if k not in same]
+    for k in keep:
+        if k != c and parent[k] in same:
+            raise ValueError(f"{path}: child of a dropped same-process span (FixSpans2 would raise KeyError)")
+    tid = spans[c]["traceID"]
+    servers, twins = [], []
+    for k in keep:
+        s = spans[k]
+        sid = tid if k == c else s["spanID"]
+        # parent position is patched below: a server's parent is its twin, a twin's parent the server
+        servers.append([tid, sid, s["startTime"], s["duration"], s["operationName"], proc[s["processID"]], "server", k])
+        if k != c:
+            twins.append([tid, sid + "_client", s["startTime"], s["duration"], s["operationName"],
+                          proc[spans[parent[k]]["processID"]], "client", k])
+    merged = servers + twins
+    merged_order = sorted(range(len(merged)), key=lambda q: merged[q][2])                # stable, by start
+    pos_server = {}
+    pos_twin = {}
+    for newpos, q in enumerate(merged_order):
+        node = merged[q]
+        (pos_server if node[6] == "server" else pos_twin)[node[7]] = newpos
+    nodes = []
+    for q in merged_order:
+        node = list(merged[q])
+        k = node[7]
+        if node[6] == "server":
+            node[7] = -1 if k == c else pos_twin[k]
+        else:
+            node[7] = pos_server[parent[k]]
+        nodes.append(node)
+    return nodes
+
+
 def load_jaeger_dir(directory: str, first_span: Optional[str] = HOTEL_FIRST_SPAN, max_traces: int = MAX_TRACES,
-                    files: Optional[Sequence[str]] = None) -> List[ServiceProblem]:
-    """All solvable services of a trace directory, in the order the reference visits them."""
+                    files: Optional[Sequence[str]] = None, layout: str = "hotel") -> List[ServiceProblem]:
+    """All solvable services of a trace directory, in the order the reference visits them.
+    layout "hotel": spans as recorded (`--fix 2`); "media": FixSpans2 rewrite (`--fix 1`, first span
+    "ComposeReview")."""
+    if layout not in ("hotel", "media"):
+        raise ValueError(f"layout {layout!r}: only the hotel (--fix 2) and media (--fix 1) layouts are built")
+    if layout == "media":
+        first_span = MEDIA_FIRST_SPAN
     files = list(files) if files is not None else trace_files(directory)
     ins: Dict[str, _Rows] = {}
     outs: Dict[str, _Rows] = {}
@@ -106,45 +189,33 @@ def load_jaeger_dir(directory: str, first_span: Optional[str] = HOTEL_FIRST_SPAN
             spans = d["spans"]
             if any(s["traceID"] != spans[0]["traceID"] for s in spans):
                 raise ValueError(f"{path}: different trace ids inside one trace")       # executor.py:372-374
-            if any(len(s["references"]) == 0 for s in spans):
+            if layout == "media" or any(len(s["references"]) == 0 for s in spans):
                 accepted.append(d)
         if len(accepted) != 1:
             raise ValueError(f"{path}: expected exactly one rooted trace (executor.py:790)")
-        d = accepted[0]
-        spans = d["spans"]
-        proc = {pid: p["serviceName"] for pid, p in d["processes"].items()}
-        index = {s["spanID"]: k for k, s in enumerate(spans)}
-        children: List[List[int]] = [[] for _ in spans]
+        nodes = _nodes_media(accepted[0], path) if layout == "media" else _nodes_plain(accepted[0], path)
+        children: List[List[int]] = [[] for _ in nodes]
         root = None
-        for k, s in enumerate(spans):
-            if len(s["references"]) == 0:
+        for k, node in enumerate(nodes):
+            if node[7] < 0:
                 root = k                                                                 # the last root wins (:822-823)
-            for ref in s["references"]:
-                children[index[ref["spanID"]]].append(k)
-        if spans[root]["operationName"] != first_span and first_span is not None:
+            else:
+                children[node[7]].append(k)
+        if first_span is not None and nodes[root][4] != first_span:
             continue
         for ch in children:
-            ch.sort(key=lambda k: spans[k]["startTime"])                                  # stable (:826-829)
-        parent = [index[s["references"][0]["spanID"]] if s["references"] else -1 for s in spans]
+            ch.sort(key=lambda k: nodes[k][2])                                           # stable (:826-829)
         stack = [root]
         while stack:                                                                     # pre-order (:831-836)
             k = stack.pop()
-            s = spans[k]
-            kind = _span_kind(s)
-            me = proc[s["processID"]]
+            tid, sid, start, dur, op, me, kind, par = nodes[k]
             if kind == "client":
                 if len(children[k]) != 1:
                     raise ValueError(f"{path}: client span with {len(children[k])} children (spans.py:33)")
-                other = proc[spans[children[k][0]]["processID"]]                         # GetChildProcess
-                outs.setdefault(me, _Rows()).add(s["startTime"], s["duration"], s["traceID"], s["spanID"], other)
+                outs.setdefault(me, _Rows()).add(start, dur, tid, sid, nodes[children[k][0]][5])   # GetChildProcess
             elif kind == "server":
-                if parent[k] < 0:
-                    other = "client_" + s["operationName"]                              # GetParentProcess, root
-                else:
-                    if len(s["references"]) != 1:
-                        raise ValueError(f"{path}: server span with several references (spans.py:41)")
-                    other = proc[spans[parent[k]]["processID"]]
-                ins.setdefault(me, _Rows()).add(s["startTime"], s["duration"], s["traceID"], s["spanID"], other)
+                other = "client_" + op if par < 0 else nodes[par][5]                      # GetParentProcess
+                ins.setdefault(me, _Rows()).add(start, dur, tid, sid, other)
             else:
                 raise ValueError(f"{path}: span.kind {kind!r} (executor.py:819)")
             stack.extend(reversed(children[k]))
