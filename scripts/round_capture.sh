@@ -8,7 +8,7 @@ python -m pytest tests -m gpu -q 2>&1 | tail -3 > gpurun_out/pytest_gpu_$R.txt
 python scripts/time_phases.py 8192 > gpurun_out/phases_$R.txt 2>&1
 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_${R}_builder.json 2> gpurun_out/bench_${R}_err.log
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_${R}_reference.json 2>> gpurun_out/bench_${R}_err.log
-ncu --metrics gpu__time_duration.sum --clock-control none -s 55 -c 80 --csv --log-file gpurun_out/launches_$R.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 45 -c 75 --csv --log-file gpurun_out/launches_$R.csv \
     python scripts/profile_run.py 8192 > gpurun_out/ncu_launch_$R.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_score2 -s 3 -c 1 -o gpurun_out/prof_${R}_score2 -f \
     python scripts/profile_run.py 2048 > gpurun_out/ncu_full_$R.log 2>&1
