@@ -59,6 +59,7 @@ struct Score2Smem {
   double prm[kPrm2];
   double tbl[kTbl2];
   unsigned long long ent_key[kEnt2];
+  unsigned long long rbest[T];
   int64_t ins[T], ine[T];
   int64_t red[T / 32];
   uint32_t ent_combo[kEnt2];
@@ -124,6 +125,7 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
   sm.ine[tid] = in_e;
   sm.nfeas[tid] = 0;
   sm.tie[tid] = 0;
+  sm.rbest[tid] = 0ULL;
   sm.rcount[tid] = 0;
 
   // ---- stage the tile's candidate slice of every ep (as k_score)
@@ -268,7 +270,7 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
     }
     if (lane == 31) { sm.scan_a[wid] = inc_t; sm.scan_b[wid] = inc_c; }
     if (tid == 0) {
-      sm.total_t = 0; sm.total_c = 0; sm.first_tid = T; sm.last_tid = -1;
+      sm.total_t = 0; sm.total_c = 0; sm.first_tid = T; sm.last_tid = -1; sm.n_ent = 0;
       sm.stream_tid = -1; sm.n_carry = 0;
     }
     __syncthreads();
@@ -285,7 +287,6 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
     const bool in_round = stream || (fits && !serial);
     sm.tstart[tid] = in_round ? toff : 0x3fffffff;
     sm.cstart[tid] = in_round ? coff : 0x3fffffff;
-    sm.rcount[tid] = in_round ? my_c : 0;          // list entries of this in-span (not used when streaming)
     if (in_round) {
       atomicMax(&sm.total_t, toff + my_t);
       atomicMax(&sm.total_c, stream ? (int)P : coff + my_c);
@@ -330,31 +331,25 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
     // ---- 2 + 3 per chunk of combinations (one chunk unless an in-span is being streamed)
     for (long long cbase = 0; cbase == 0 || cbase < total_c; cbase += chunk) {
       const int cend = (int)(cbase + chunk < (long long)total_c ? cbase + chunk : (long long)total_c);
-      if (cbase > 0) {   // streaming: the running top-K re-enters the list, in front of the chunk
+      if (cbase > 0) {   // streaming: the running top-K re-enters the list
         if (tid < sm.n_carry) {
           sm.ent_key[tid] = sm.carry_key[tid];
           sm.ent_combo[tid] = sm.carry_combo[tid];
           sm.ent_j[tid] = (uint16_t)stream_tid;
         }
+        if (tid == 0) sm.n_ent = sm.n_carry;
         __syncthreads();
       }
-      const int list_off = cbase > 0 ? sm.n_carry : 0;
-      const int n_list = list_off + (cend - (int)cbase);
-      // ---- 2. combinations: feasibility, score, list entry, candidate bitmap.  Combination g owns
-      // list slot list_off + g - cbase, so the entries of an in-span are contiguous.
+      // ---- 2. combinations: feasibility, score, list entry, candidate bitmap
       for (int g = (int)cbase + tid; g < cend; g += T) {
         const int j = stream_tid >= 0 ? stream_tid : owner_of(sm.cstart, g);
-        const int slot = list_off + (g - (int)cbase);
         int lo_rel[TW_MAX_E], o_last[TW_MAX_E], c[TW_MAX_E];
         int64_t ce[TW_MAX_E];
         for (int e = 0; e < E; ++e) lo_rel[e] = sm.lo_abs[j][e] - sm.win[e].base;
         term_table_last_offsets(v, sm.rr[j], o_last);
         const int combo = g - sm.cstart[j];
         const double* tbl = sm.tbl + sm.tstart[j];
-        if (!combo_feasible(v, sm.win, lo_rel, sm.rr[j], o_last, sm.sid + sm.tstart[j], combo, c, ce)) {
-          sm.ent_key[slot] = 0ULL;
-          continue;
-        }
+        if (!combo_feasible(v, sm.win, lo_rel, sm.rr[j], o_last, sm.sid + sm.tstart[j], combo, c, ce)) continue;
         atomicAdd(&sm.nfeas[j], 1);
         for (int e = 0; e < E; ++e) {
           int bit = c[e] - sm.lo_abs[j][e];
@@ -363,48 +358,52 @@ k_score2(tw_batch b, tw_params prm, tw_score_out out, TileList tiles, const int3
         }
         unsigned long long key = score_key(table_score(v, sm.rr[j], sm.lo_abs[j], tbl, c, ce));
         if (key == 0ULL) key = 1ULL;
+        const int slot = atomicAdd(&sm.n_ent, 1);
         sm.ent_key[slot] = key;
         sm.ent_combo[slot] = (uint32_t)combo;
         sm.ent_j[slot] = (uint16_t)j;
       }
       __syncthreads();
   TW_PHASE(5);
-      // ---- 3. top-K by ranking: an entry's rank is the number of entries of its in-span with a
-      // larger key (the scan stops at K of them).  Rank < K: it is written out at that rank — unless
-      // another entry has the same key, in which case the owner redoes the in-span sequentially to
-      // get the reference's tie order.
-      for (int en = tid; en < n_list; en += T) {
-        const unsigned long long key = sm.ent_key[en];
-        if (key == 0ULL) continue;
-        const int j = sm.ent_j[en];
-        const int qa = stream_tid >= 0 ? 0 : sm.cstart[j];
-        const int qz = stream_tid >= 0 ? n_list : qa + sm.rcount[j];
-        int larger = 0;
-        bool tied = false;
-        for (int q = qa; q < qz && larger < TW_K; ++q) {
-          const unsigned long long k2 = sm.ent_key[q];
-          larger += k2 > key ? 1 : 0;
-          tied |= k2 == key && q != en;
+      // ---- 3. top-K: K rounds of segmented arg-max over the list
+      const int n_ent = sm.n_ent;
+      int ranks_done = 0;
+      for (int rk = 0; rk < TW_K; ++rk) {
+        bool any = false;
+        for (int en = tid; en < n_ent; en += T) {
+          const unsigned long long key = sm.ent_key[en];
+          if (key != 0ULL) { atomicMax(&sm.rbest[sm.ent_j[en]], key); any = true; }
         }
-        if (larger >= TW_K) continue;
-        if (tied) { sm.tie[j] = 1; continue; }
-        const int ij = i0 + j;
-        const int64_t gi = v.in_off + ij;
-        out.topk_score[gi * TW_K + larger] = key_to_score(key);
-        int32_t* ix = out.topk_idx + TW_K * (v.tuple_off + (int64_t)ij * E) + larger * E;
-        unsigned idx = sm.ent_combo[en];
-        for (int e = E - 1; e >= 0; --e) {
-          const unsigned re = (unsigned)sm.rr[j][e], q = idx / re;
-          ix[e] = sm.lo_abs[j][e] + (int)(idx - q * re);
-          idx = q;
+        if (!__syncthreads_or(any)) break;
+        ranks_done = rk + 1;
+        for (int en = tid; en < n_ent; en += T) {
+          const unsigned long long key = sm.ent_key[en];
+          const int j = sm.ent_j[en];
+          if (key != 0ULL && key == sm.rbest[j]) {
+            if (atomicAdd(&sm.rcount[j], 1) == 0) {   // winner of rank rk for in-span j
+              sm.ent_key[en] = 0ULL;
+              const int ij = i0 + j;
+              const int64_t gi = v.in_off + ij;
+              out.topk_score[gi * TW_K + rk] = key_to_score(key);
+              int32_t* ix = out.topk_idx + TW_K * (v.tuple_off + (int64_t)ij * E) + rk * E;
+              unsigned idx = sm.ent_combo[en];
+              for (int e = E - 1; e >= 0; --e) {
+                const unsigned re = (unsigned)sm.rr[j][e], q = idx / re;
+                ix[e] = sm.lo_abs[j][e] + (int)(idx - q * re);
+                idx = q;
+              }
+              if (stream_tid >= 0) { sm.carry_key[rk] = key; sm.carry_combo[rk] = sm.ent_combo[en]; }
+            } else {
+              sm.tie[j] = 1;   // two tuples with the same score: keep the reference's tie order
+            }
+          }
         }
-        if (stream_tid >= 0) { sm.carry_key[larger] = key; sm.carry_combo[larger] = sm.ent_combo[en]; }
-      }
-      __syncthreads();
-      if (stream_tid >= 0) {
-        if (tid == 0) sm.n_carry = sm.nfeas[stream_tid] < TW_K ? sm.nfeas[stream_tid] : TW_K;
+        __syncthreads();
+        if (in_round) { sm.rbest[tid] = 0ULL; sm.rcount[tid] = 0; }
         __syncthreads();
       }
+      if (tid == 0) sm.n_carry = ranks_done;
+      __syncthreads();
   TW_PHASE(6);
       if (chunk == 0x7fffffff) break;
     }
