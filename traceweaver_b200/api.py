@@ -35,6 +35,8 @@ class BatchSolver:
 
     #: below this many in-spans a batch is solved in one piece (copies are not worth hiding)
     MIN_CHUNK_IN_SPANS = 1 << 20
+    #: share of the in-spans in the first of two groups
+    FIRST_GROUP_FRACTION = 0.5
 
     def __init__(self, device=0, seed_select=10, chunks=2):
         self.engine = Engine(device)
@@ -42,6 +44,7 @@ class BatchSolver:
         self.chunks = max(1, int(chunks))
         self._engines = [self.engine]
         self._streams = None
+        self._copy_stream = None
         self._pinned_in = {}
         self._pinned_out = {}
         self._plan = None
@@ -80,8 +83,11 @@ class BatchSolver:
             if C == 1:
                 plan = [(0, hb.n_problems, hb)]
             else:
-                # equal in-span counts per group
-                cuts = np.searchsorted(hb.prob_in_off, np.arange(1, C) * (n_in / C), side="left")
+                # a small first group (its host->device copy is the only one nothing can hide), the
+                # rest in equal in-span counts
+                first = self.FIRST_GROUP_FRACTION if C == 2 else 1.0 / C
+                fr = first + (1.0 - first) * np.arange(0, C - 1) / max(C - 1, 1)
+                cuts = np.searchsorted(hb.prob_in_off, fr * n_in, side="left")
                 edges = sorted(set([0, hb.n_problems] + [int(c) for c in cuts if 0 < c < hb.n_problems]))
                 plan = [(lo, hi, hb.slice(lo, hi)) for lo, hi in zip(edges[:-1], edges[1:])]
             self._plan = (key, plan)
@@ -94,6 +100,8 @@ class BatchSolver:
         if len(plan) > 1 and self._streams is None:
             self._engines.append(Engine(dev.index if dev.index is not None else 0))
             self._streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(dev)
         n_in, n_tuple = int(hb.prob_in_off[-1]), int(hb.prob_tuple_off[-1])
         out = dict(
             assign=self._out_buf("assign", n_tuple, torch.int32),
@@ -123,16 +131,31 @@ class BatchSolver:
                         np.ascontiguousarray(truth_assign, np.int32)).to(dev)
                     to = None if term_order is None else torch.from_numpy(
                         np.ascontiguousarray(term_order, np.int32)).to(dev)
-                res = solve_bound(eng, seed_select=self.seed_select, truth_assign=ta, term_order=to, check=False)
                 i0, t0 = int(hb.prob_in_off[lo]), int(hb.prob_tuple_off[lo])
                 i1, t1 = int(hb.prob_in_off[hi]), int(hb.prob_tuple_off[hi])
-                for name, (b0, b1) in (("assign", (t0, t1)), ("topk_idx", (_abi.TW_K * t0, _abi.TW_K * t1)),
-                                       ("topk_cnt", (i0, i1)), ("n_cand", (i0, i1)), ("counters", (lo, hi)),
+
+                def copy_topk(top, stream=stream, i0=i0, i1=i1, t0=t0, t1=t1):
+                    # the top-K lists (three quarters of the result bytes) are final before the last
+                    # stitch: copy them out on the copy stream while that kernel runs
+                    ev = torch.cuda.Event()
+                    ev.record(stream)
+                    self._copy_stream.wait_event(ev)
+                    with torch.cuda.stream(self._copy_stream):
+                        for name, (b0, b1) in (("topk_idx", (_abi.TW_K * t0, _abi.TW_K * t1)), ("topk_cnt", (i0, i1))):
+                            t = top[name]
+                            t.record_stream(self._copy_stream)
+                            out[name][b0:b1].copy_(t, non_blocking=True)
+
+                res = solve_bound(eng, seed_select=self.seed_select, truth_assign=ta, term_order=to, check=False,
+                                  after_score=copy_topk)
+                d2h += sum(res[k].numel() * res[k].element_size() for k in ("topk_idx", "topk_cnt"))
+                for name, (b0, b1) in (("assign", (t0, t1)), ("n_cand", (i0, i1)), ("counters", (lo, hi)),
                                        ("mis_rank", (i0, i1))):
                     t = res[name]
                     out[name][b0:b1].copy_(t, non_blocking=True)  # D2H
                     d2h += t.numel() * t.element_size()
             used.append((eng, stream))
+        self._copy_stream.synchronize()
         for eng, stream in dict((id(e), (e, s)) for e, s in used).values():
             with torch.cuda.stream(stream):
                 eng.status()                                      # syncs the stream, raises on engine errors

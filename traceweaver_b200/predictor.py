@@ -29,9 +29,11 @@ def solve_batch(eng: Engine, hb, seed_select=10, truth_assign=None, term_order=N
     return solve_bound(eng, seed_select, truth_assign, term_order)
 
 
-def solve_bound(eng: Engine, seed_select=10, truth_assign=None, term_order=None, check=True):
+def solve_bound(eng: Engine, seed_select=10, truth_assign=None, term_order=None, check=True, after_score=None):
     """Both passes over the batch currently bound to `eng` (inputs resident in HBM).  check=False
-    leaves the one host sync (engine status) to the caller, who must call eng.status()."""
+    leaves the one host sync (engine status) to the caller, who must call eng.status().
+    `after_score(top)` is called as soon as the final top-K lists are queued (before the last
+    stitch), so a caller can start copying them out while the stitch runs."""
     eng.prepare()                                 # prev-index scan, sorted end times
     p0 = eng.params_pass0()                       # ComputeEpPairDistParams3, every 100-span batch
     # CreateWindows2 (perfect-cut flags) + FindTopKAssignments on the undeleted lists, pass-0 params
@@ -47,6 +49,8 @@ def solve_bound(eng: Engine, seed_select=10, truth_assign=None, term_order=None,
     p1 = eng.gmm_refit(delays, counts, seed_select=seed_select, prob_base_skip=base, term_order=term_order)
     # top_k_2 of the last iteration -> all_topk_assignments; candidate maps are parameter independent
     top = eng.score(p1, out=dict(used_lo=sc["used_lo"], used_bits=sc["used_bits"], used_wide=sc["used_wide"]))
+    if after_score is not None:
+        after_score(top)
     r1 = eng.stitch(p1, sc["cut"], undeleted=top)  # iteration 1
     n_cand = r0["n_cand"] + r1["n_cand"]          # per_span_candidates accumulates over iterations
     if check:
