@@ -86,23 +86,16 @@ struct ScoreSmem {
   double etab[64];
 };
 
+// one tile (index t of `tiles`) by the whole CTA
 template <int T, int W>
-__global__ void __launch_bounds__(T)
-k_score(tw_batch b, tw_params prm, int has_params, tw_score_out out, TileList tiles,
-        const int32_t* __restrict__ prev_idx, uint8_t* __restrict__ overflow_flag, int redo_only,
-        int* __restrict__ err_flag) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  ScoreSmem<T, W>& sm = *reinterpret_cast<ScoreSmem<T, W>*>(smem_raw);
+__device__ __forceinline__ void score_tile(const tw_batch& b, const tw_params& prm, int has_params,
+                                           const tw_score_out& out, const TileList& tiles, int t,
+                                           const int32_t* __restrict__ prev_idx,
+                                           uint8_t* __restrict__ overflow_flag, int redo_only,
+                                           int* __restrict__ err_flag, ScoreSmem<T, W>& sm) {
   const int tid = threadIdx.x;
-  const int t = blockIdx.x;
   int i0, cnt, p;
   if (tid < 64) sm.etab[tid] = c_exp2_64[tid];   // visible after the barrier below (load_view)
-  if (redo_only) {
-    // wide pass: narrow tile `blockIdx.y`-independent mapping — wide tiles subdivide narrow ones
-    // tiles.tile_prob/tile_start describe WIDE tiles; overflow_flag is indexed by the narrow tile
-    // each wide tile belongs to (stored in the upper entries of tile arrays by the host).
-    if (!overflow_flag[tiles.tile_start[tiles.n_tiles + t]]) return;
-  }
   p = tiles.tile_prob[t];
   i0 = tiles.tile_start[t];
 
@@ -358,6 +351,28 @@ k_score(tw_batch b, tw_params prm, int has_params, tw_score_out out, TileList ti
   }
 }
 
+// Normal launches: CTA t owns tile t.  The wide redo pass (redo_only) runs a FIXED grid whose CTAs
+// stride over the wide tiles and only work on those whose narrow tile overflowed
+// (tiles.tile_start[n_tiles + t] = narrow tile of wide tile t): overflow is rare, and one CTA per
+// wide tile meant a quarter of a million CTAs that exit at once (1.9 ms per pass at 8192 services).
+template <int T, int W>
+__global__ void __launch_bounds__(T)
+k_score(tw_batch b, tw_params prm, int has_params, tw_score_out out, TileList tiles,
+        const int32_t* __restrict__ prev_idx, uint8_t* __restrict__ overflow_flag, int redo_only,
+        int* __restrict__ err_flag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ScoreSmem<T, W>& sm = *reinterpret_cast<ScoreSmem<T, W>*>(smem_raw);
+  if (!redo_only) {
+    score_tile<T, W>(b, prm, has_params, out, tiles, blockIdx.x, prev_idx, overflow_flag, 0, err_flag, sm);
+    return;
+  }
+  for (int t = blockIdx.x; t < tiles.n_tiles; t += gridDim.x) {
+    if (!overflow_flag[tiles.tile_start[tiles.n_tiles + t]]) continue;   // uniform across the CTA
+    score_tile<T, W>(b, prm, has_params, out, tiles, t, prev_idx, overflow_flag, 1, err_flag, sm);
+    __syncthreads();                                                      // shared memory is re-used
+  }
+}
+
 cudaError_t launch_score(const tw_batch& b, const tw_params* prm, const tw_score_out& out,
                          const TileList& narrow, const TileList& wide, const int32_t* prev_idx,
                          uint8_t* narrow_overflow, int* err_flag, cudaStream_t s, bool wide_only) {
@@ -386,8 +401,9 @@ cudaError_t launch_score(const tw_batch& b, const tw_params* prm, const tw_score
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
-  kw<<<wide.n_tiles, kWideThreads, sizeof(SmW), s>>>(b, pr, prm != nullptr, out, wide, prev_idx,
-                                                     narrow_overflow, 1, err_flag);
+  const int wide_grid = wide.n_tiles < 148 * 16 ? wide.n_tiles : 148 * 16;
+  kw<<<wide_grid, kWideThreads, sizeof(SmW), s>>>(b, pr, prm != nullptr, out, wide, prev_idx,
+                                                  narrow_overflow, 1, err_flag);
   return cudaGetLastError();
 }
 
