@@ -13,7 +13,6 @@ constexpr int kScoreTile = kScoreThreads - 1;    // in-spans per CTA; the last t
                                                  // the tile's carry-in "prev" in-span (PerfectCut)
 constexpr int kStageSpans = 1536;                // out spans staged in shared memory per tile
 constexpr int kTblCap = 3072;                    // term-table slots per CTA round (tw_core.cuh)
-constexpr int kLightCombos = 12;                 // more candidate combinations -> warp-cooperative enumeration
 constexpr int kWarpTblCap = 192;                 // term-table slots per stitch warp (search path only)
 constexpr int kTakenWords = 256;                 // taken-bitmap words a stitch warp keeps in shared memory
 constexpr int kNarrowW = 2;                      // bitmap words per (in-span, ep): 64 candidates

@@ -8,10 +8,6 @@ import torch
 from . import _abi, _lib
 from .batch import HostBatch, batch_struct
 
-_NP2TORCH = {np.dtype(np.int64): torch.int64, np.dtype(np.int32): torch.int32,
-             np.dtype(np.uint32): torch.int32, np.dtype(np.int8): torch.int8,
-             np.dtype(np.uint8): torch.uint8, np.dtype(np.float64): torch.float64}
-
 
 def _to_device(a: np.ndarray, device, pinned=False):
     if a.dtype == np.uint32:
