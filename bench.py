@@ -134,8 +134,20 @@ def run_ours(args):
     rank, local_rank, world = dist_env()
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # stdout carries the one JSON line only: NCCL prints its version banner with printf when the
+        # first communicator is created, so stdout points at stderr until that has happened
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            warm = torch.zeros(1, device=torch.device("cuda", local_rank))
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     dev = torch.device("cuda", local_rank)
 
     # ---- this rank's shard of the stream (synthetic, seeded; generation is not timed)
