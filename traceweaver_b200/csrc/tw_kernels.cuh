@@ -20,7 +20,7 @@ constexpr int kWideW = 64;                       // overflow kernel: 2048 candid
 constexpr int kWideThreads = 32;                 // (31 in-spans + carry-in per CTA)
 
 // ---- stitch kernel geometry (tw_stitch.cu) --------------------------------------------------
-constexpr int kStitchWarps = 4;                  // one warp per problem
+constexpr int kStitchWarps = 2;                  // one warp per problem
 
 struct EngineScratch;                            // tw_api.cu
 
