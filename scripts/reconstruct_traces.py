@@ -1,6 +1,6 @@
 """Reconstruct a directory of Jaeger JSON traces end to end: loader -> batch engine -> accuracy.
 
-    python scripts/reconstruct_traces.py <trace dir> [--layout hotel|media] [--device 0]
+    python scripts/reconstruct_traces.py <trace dir> [--layout hotel|media|node] [--device 0]
 
 Prints, per solved service, the assignment accuracy against the traces' own parent links
 (the reference's AccuracyForService, helpers/utils.py:34-60) and the time of each stage — the same
@@ -11,7 +11,7 @@ import numpy as np
 
 ap = argparse.ArgumentParser()
 ap.add_argument("directory")
-ap.add_argument("--layout", default="hotel", choices=["hotel", "media"])
+ap.add_argument("--layout", default="hotel", choices=["hotel", "media", "node"])
 ap.add_argument("--device", type=int, default=0)
 ap.add_argument("--seed", type=int, default=10)
 args = ap.parse_args()

@@ -22,16 +22,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_ROOT = "/root/reference/data"
 REF_DATA = os.path.join(REF_ROOT, "hotel_reservation")
 GOLDENS = sorted(glob.glob(os.path.join(HERE, "golden", "hotel_load*__*.npz")) +
-                 glob.glob(os.path.join(HERE, "golden", "media_load*__*.npz")))
+                 glob.glob(os.path.join(HERE, "golden", "media_load*__*.npz")) +
+                 glob.glob(os.path.join(HERE, "golden", "node_load*__*.npz")))
 _cache = {}
 
 
 def _services(dataset):
     from traceweaver_b200.loader import load_jaeger_dir
     if dataset not in _cache:
-        media = dataset.startswith("media")
-        d = os.path.join(REF_ROOT, "media_microservices" if media else "hotel_reservation", dataset)
-        _cache[dataset] = {s.name: s for s in load_jaeger_dir(d, layout="media" if media else "hotel")}
+        layout = dataset.split("_")[0]
+        sub = {"hotel": "hotel_reservation", "media": "media_microservices", "node": "nodejs_microservices"}[layout]
+        _cache[dataset] = {s.name: s for s in load_jaeger_dir(os.path.join(REF_ROOT, sub, dataset), layout=layout)}
     return _cache[dataset]
 
 

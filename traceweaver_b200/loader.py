@@ -7,8 +7,9 @@ ProcessTraceData :798-848, the per-service loop :1080-1140, utils.GetGroundTruth
 FindOrder executor.py:214-285).  This module restates that data path for two of the reference's
 dataset layouts — "hotel": spans as recorded (`--fix 2` hotel_reservation, first span
 "HTTP GET /hotels"; any dataset whose spans carry `span.kind` client/server tags), "media": the
-FixSpans2 rewrite (`--fix 1` media_microservices, executor.py:539-640) — and emits, per solved
-service, exactly what the engine binds:
+FixSpans2 rewrite (`--fix 1` media_microservices, executor.py:539-640), "node": the FixSpans rewrite
+(`--fix 0` nodejs_microservices, executor.py:511-537) — and emits, per solved service, exactly what
+the engine binds:
 
     in_start / in_end            int64 [n]      the service's server spans, sorted by (start, end)
     out_start[e] / out_end[e]    int64 [n_e]    client spans per callee, same sort, callees in the
@@ -21,8 +22,8 @@ Same order-defining rules as the reference, because ties in `start` are broken b
 files by root start time (np.argsort, executor.py:305-309), spans of a trace in pre-order with
 children sorted by start (:826-836), partitions stable-sorted by (start, end) (:1107), the trace
 cap `cnt > 1000` (:873).  tests/test_loader.py checks the output against the goldens minted from
-the reference's own loader (12 hotel + 6 media services: arrays, ids, graph, ground truth equal).
-Not built: `--fix 0/3/4/5` (nodejs FixSpans, Alibaba self-loop rewriting).
+the reference's own loader (12 hotel + 6 media + 4 nodejs services: arrays, ids, graph, ground
+truth equal).  Not built: `--fix 3/4/5` (other entry operations, Alibaba self-loop rewriting).
 """
 import json
 import os
@@ -35,6 +36,7 @@ from .batch import Problem, build_batch
 
 HOTEL_FIRST_SPAN = "HTTP GET /hotels"          # executor.py:759 (--fix 2)
 MEDIA_FIRST_SPAN = "ComposeReview"             # executor.py:758 (--fix 1)
+NODE_FIRST_SPAN = "init-span"                  # executor.py:757 (--fix 0)
 MAX_TRACES = 1000                              # executor.py:873: stop once cnt > 1000
 
 
@@ -110,6 +112,37 @@ def _nodes_plain(d, path):
     return nodes
 
 
+def _nodes_node(d, path):
+    """FixSpans (executor.py:511-537), the `--fix 0` rewrite of the nodejs_microservices traces: the
+    root "init-span" (recorded as a client span) becomes a server span, every recorded server span
+    gets a client twin with the same timing in its caller's process.  The reference looks the
+    caller up in a static service table (executor.py:109-115); the parent span's own process is the
+    same service in these traces.  Dict order: recorded spans, then the twins, both in JSON order."""
+    spans = d["spans"]
+    proc = {pid: p["serviceName"] for pid, p in d["processes"].items()}
+    index = {s["spanID"]: k for k, s in enumerate(spans)}
+    n = len(spans)
+    nodes, twins = [], []
+    for k, s in enumerate(spans):
+        if len(s["references"]) > 1:
+            raise ValueError(f"{path}: span with several references (spans.py:41)")
+        kind = _span_kind(s)
+        par = index[s["references"][0]["spanID"]] if s["references"] else -1
+        base = [s["traceID"], s["spanID"], s["startTime"], s["duration"], s["operationName"], proc[s["processID"]]]
+        if kind == "client":
+            nodes.append(base + ["server", par])
+        elif kind == "server":
+            if par < 0:
+                raise ValueError(f"{path}: server span without a parent (FixSpans indexes references[0])")
+            twin_pos = n + len(twins)
+            nodes.append(base + ["server", twin_pos])
+            twins.append([s["traceID"], s["spanID"] + "_client", s["startTime"], s["duration"], s["operationName"],
+                          proc[spans[par]["processID"]], "client", par])
+        else:
+            nodes.append(base + [kind, par])
+    return nodes + twins
+
+
 def _nodes_media(d, path):
     """FixSpans2 (executor.py:539-640), the `--fix 1` rewrite of media_microservices traces, whose
     spans carry no span.kind: the "ComposeReview" span becomes the root (its ancestors are dropped,
@@ -172,11 +205,13 @@ def load_jaeger_dir(directory: str, first_span: Optional[str] = HOTEL_FIRST_SPAN
                     files: Optional[Sequence[str]] = None, layout: str = "hotel") -> List[ServiceProblem]:
     """All solvable services of a trace directory, in the order the reference visits them.
     layout "hotel": spans as recorded (`--fix 2`); "media": FixSpans2 rewrite (`--fix 1`, first span
-    "ComposeReview")."""
-    if layout not in ("hotel", "media"):
-        raise ValueError(f"layout {layout!r}: only the hotel (--fix 2) and media (--fix 1) layouts are built")
+    "ComposeReview"); "node": FixSpans rewrite (`--fix 0`, first span "init-span")."""
+    if layout not in ("hotel", "media", "node"):
+        raise ValueError(f"layout {layout!r}: only the hotel (--fix 2), media (--fix 1) and node (--fix 0) layouts are built")
     if layout == "media":
         first_span = MEDIA_FIRST_SPAN
+    if layout == "node":
+        first_span = NODE_FIRST_SPAN
     files = list(files) if files is not None else trace_files(directory)
     ins: Dict[str, _Rows] = {}
     outs: Dict[str, _Rows] = {}
@@ -193,7 +228,7 @@ def load_jaeger_dir(directory: str, first_span: Optional[str] = HOTEL_FIRST_SPAN
                 accepted.append(d)
         if len(accepted) != 1:
             raise ValueError(f"{path}: expected exactly one rooted trace (executor.py:790)")
-        nodes = _nodes_media(accepted[0], path) if layout == "media" else _nodes_plain(accepted[0], path)
+        nodes = {"media": _nodes_media, "node": _nodes_node, "hotel": _nodes_plain}[layout](accepted[0], path)
         children: List[List[int]] = [[] for _ in nodes]
         root = None
         for k, node in enumerate(nodes):
