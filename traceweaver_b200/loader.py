@@ -341,3 +341,46 @@ def accuracy(service: ServiceProblem, assign: np.ndarray) -> float:
     is right at EVERY callee.  `assign` is the engine's [E, n] block of this service."""
     ok = (np.asarray(assign).reshape(service.truth.shape) == service.truth).all(axis=0)
     return float(ok.mean()) if ok.size else 0.0
+
+
+# ---------------------------------------------------------------------------------------------
+# Accuracy on index arrays (helpers/utils.py:34-145), per service and per trace.  `truth`, `assign`
+# are int32 [E, n]; `topk_idx` is [n, K, E] with `topk_cnt[i]` valid ranks; `in_trace[i]` the trace id.
+# ---------------------------------------------------------------------------------------------
+def topk_accuracy(truth: np.ndarray, topk_idx: np.ndarray, topk_cnt: np.ndarray) -> float:
+    """utils.TopKAccuracyForService: an in-span counts when SOME rank matches the truth at every callee."""
+    truth = np.asarray(truth)
+    hit = (np.asarray(topk_idx) == truth.T[:, None, :]).all(axis=2)              # [n, K]
+    valid = np.arange(hit.shape[1])[None, :] < np.asarray(topk_cnt)[:, None]
+    ok = (hit & valid).any(axis=1)
+    return float(ok.mean()) if ok.size else 0.0
+
+
+def end_to_end_accuracy(in_traces: Sequence[Sequence[str]], truths: Sequence[np.ndarray],
+                        assigns: Sequence[np.ndarray]) -> float:
+    """utils.AccuracyEndToEnd over the solved services: a trace is right when every in-span it has
+    in any of them got all its children right."""
+    acc: Dict[str, bool] = {}
+    for tids, truth, assign in zip(in_traces, truths, assigns):
+        ok = (np.asarray(assign).reshape(np.asarray(truth).shape) == truth).all(axis=0)
+        for t, good in zip(tids, ok):
+            acc[t] = acc.get(t, True) and bool(good)
+    return sum(acc.values()) / len(acc) if acc else 0.0
+
+
+def end_to_end_topk_accuracy(in_traces: Sequence[Sequence[str]], truths: Sequence[np.ndarray],
+                             topk_idxs: Sequence[np.ndarray], topk_cnts: Sequence[np.ndarray]) -> float:
+    """utils.TopKAccuracyEndToEnd, with its order dependence: services in the given order; in the first
+    service an in-span sets its trace's flag (the last in-span of the trace wins), in later services an
+    in-span only touches traces that are still right."""
+    acc: Dict[str, bool] = {}
+    for s, (tids, truth, idx, cnt) in enumerate(zip(in_traces, truths, topk_idxs, topk_cnts)):
+        truth = np.asarray(truth)
+        hit = (np.asarray(idx) == truth.T[:, None, :]).all(axis=2)
+        valid = np.arange(hit.shape[1])[None, :] < np.asarray(cnt)[:, None]
+        ok = (hit & valid).any(axis=1)
+        for t, good in zip(tids, ok):
+            if s != 0 and acc[t] is False:
+                continue
+            acc[t] = bool(good)
+    return sum(acc.values()) / len(acc) if acc else 0.0
