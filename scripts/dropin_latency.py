@@ -11,7 +11,7 @@ from traceweaver_b200.predictor import TraceWeaverV3
 
 pred = TraceWeaverV3({}, {}, device=0)
 tot_ref = tot_us = 0.0
-for f in golden_files():
+for f in golden_files(gpu=True):
     g = Golden(f)
     args = reference_call_args(g)
     for _ in range(2):   # second call: steady state (allocations, caches warm)

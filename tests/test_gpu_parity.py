@@ -9,7 +9,7 @@ from golden_util import Golden, golden_files
 
 pytestmark = pytest.mark.gpu
 
-FILES = golden_files()
+FILES = golden_files(gpu=True)
 IDS = [f.split("/")[-1][:-4] for f in FILES]
 SCORE_TOL = 1e-5
 
