@@ -2,10 +2,10 @@
 sample (7 distinct values) depends on the ORDER of the samples: same multiset, same starting point,
 different summation order inside `resp.T @ (X * X)`.
 
-    python scripts/gmm_conditioning.py [tests/golden/node_load50__service2.npz] [term]
+    python tests/gmm_conditioning.py [tests/golden/node_load50__service2.npz] [term]
 """
 import os, sys, warnings
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))      # test tooling: may use oracle/
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 warnings.filterwarnings("ignore")
 import numpy as np

@@ -15,7 +15,7 @@ IDS = [f.split("/")[-1][:-4] for f in FILES]
 # distinct delay values (multiples of 1000 us); with k >= 4 components collapse onto single values and
 # scikit-learn's diagonal covariance avg(X^2) - mean^2 + 1e-6 cancels 3.6e7 against itself, so the
 # fitted covariance — and the BIC — depend on the BLAS summation order: scikit-learn's OWN BIC for these
-# samples moves by +-11 when the sample list is merely permuted (scripts/gmm_conditioning.py), while the
+# samples moves by +-11 when the sample list is merely permuted (tests/gmm_conditioning.py), while the
 # recorded K = 4 vs K = 5 gap is 8.  A restatement with another summation order lands on the other side.
 # The selection of these terms is not compared; everything else of the fixture is.
 ILL_CONDITIONED = {"node_load50__service2": [1], "node_load75__service1": [1]}
