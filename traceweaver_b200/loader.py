@@ -23,7 +23,9 @@ files by root start time (np.argsort, executor.py:305-309), spans of a trace in 
 children sorted by start (:826-836), partitions stable-sorted by (start, end) (:1107), the trace
 cap `cnt > 1000` (:873).  tests/test_loader.py checks the output against the goldens minted from
 the reference's own loader (12 hotel + 6 media + 4 nodejs services: arrays, ids, graph, ground
-truth equal).  Not built: `--fix 3/4/5` (other entry operations, Alibaba self-loop rewriting).
+truth equal).  `--fix 3` / `--fix 4` are the "hotel" layout with another `first_span` (no span
+rewrite, executor.py:760-761; not checked against goldens — no such dataset is shipped).  Not built:
+`--fix 5` (Alibaba: no first-span filter, self-loop rewriting, executor.py:386-400).
 """
 import json
 import os
