@@ -1,21 +1,31 @@
 #!/usr/bin/env python
 """bench.py — spans/sec of the span-assignment hot path (TraceWeaverV3.FindAssignments,
-BASELINE.json north_star) on a hotel_reservation-shaped synthetic span stream.
+BASELINE.json north_star) on synthetic span streams of the shapes BASELINE.json names.
 
-    python bench.py --gpus N --steps K --warmup W                # ours (CUDA engine via the C ABI)
-    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm: the reference's algorithm
-                                                                  # (oracle/ C port, all host threads)
+    python bench.py --gpus N --steps K --warmup W                     # ours (CUDA engine via the C ABI)
+    python bench.py --impl reference --gpus N --steps K --warmup W    # CPU arm: the reference's algorithm
+                                                                      # (oracle/ C port, host cores)
+    --workload {hotel,media,alibaba}   stream shape of the headline line (default hotel = configs[1] shape)
+    --scaling {weak,strong}            weak: 8192 services per GPU; strong: ONE fixed list (--spans, default 100 M)
+    --no-extra                         skip the extra_workloads legs (media-shaped, alibaba-shaped, shipped traces)
 
-One "step" = one pass of the whole path (both iterations + GMM refit) over this rank's batch of
-services.  Ranks own disjoint services (the stream shards by service, no data-path collective):
-weak scaling, value = spans of all ranks / max-over-ranks time.  Prints ONE JSON line on rank 0.
+One "step" = one pass of the whole path (both iterations + GMM refit) over the service list.  The
+list is ONE global list partitioned across the ranks by span count (traceweaver_b200.shard); every
+step ends with the path's single collective, an all-gather of the per-service assignment arrays
+(NCCL), inside the timed region.  value = spans of the whole list / max-over-ranks time.  Prints ONE
+JSON line on rank 0.
 
   value      device-timed throughput with the span arrays already resident in HBM
-  e2e        the same metric through the public batch API with HOST buffers: pinned H2D of the
-             span arrays and D2H of assignments / top-K / counters inside the timed region
-  roofline   score kernel (k_score, GMM pass): algorithmic bytes / CUDA-event time / measured HBM peak
+  e2e        the same metric through the public batch API with HOST buffers: every step copies the
+             caller's arrays into pinned staging (host memcpy), H2D, solves, D2H of assignments /
+             top-K / counters — all inside the timed region; inputs are rewritten in place between
+             steps so nothing can be cached
+  roofline   scoring kernel (k_score3, GMM pass = the final top-K lists): algorithmic bytes /
+             CUDA-event time / measured HBM peak
   cpu_baseline   oracle/ (C restatement of the reference, kind "port") on a bounded sample of the
-             same services, all host threads, rank 0 at N=1
+             same services, one thread per physical core, rank 0 at N=1
+  extra_workloads (N=1): the same measurements on the media-shaped and alibaba-shaped streams and on
+             the shipped Jaeger directories (the problems of tests/golden, hotel x12 / media / nodejs)
 """
 import argparse
 import json
@@ -32,6 +42,15 @@ sys.path.insert(0, ROOT)
 
 METRIC = "spans/sec reconstructed (in+out spans of all solved services)"
 UNIT = "spans/s"
+WORKLOAD_TEXT = {
+    "hotel": "hotel_reservation-shaped synthetic span stream (BASELINE configs[1] shape: frontend E=3 chain+"
+             "transitive edge, search E=2 chain; six load levels 25..150; log-normal delays calibrated on the "
+             "reference traces)",
+    "media": "media_microservices-shaped synthetic span stream (BASELINE configs[2] shape: nginx E=4 parallel, "
+             "movie-id E=2 parallel, four one-callee services; loads 25..150; calibrated on media_load100)",
+    "alibaba": "alibaba-shaped synthetic window (BASELINE configs[3]; the trace is not shipped): 1..4 callees, "
+               "millisecond clocks, exps/exp5 time compression as load",
+}
 
 
 def parse():
@@ -40,26 +59,19 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--services", type=int, default=8192, help="services per GPU")
+    ap.add_argument("--workload", default="hotel", choices=["hotel", "media", "alibaba"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--services", type=int, default=8192, help="services per GPU (weak scaling)")
+    ap.add_argument("--spans", type=int, default=100_000_000, help="total spans of the list (strong scaling)")
     ap.add_argument("--n-in", type=int, default=1000, help="incoming spans per service")
-    ap.add_argument("--cpu-sample", type=int, default=192, help="services in the CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=384, help="services in the CPU-baseline sample")
+    ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--seed", type=int, default=10)
     return ap.parse_args()
 
 
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-
-
-def workload_config(args, world, hb, n_spans):
-    return {"workload": "hotel_reservation-shaped synthetic span stream (BASELINE configs[1] shape: frontend E=3 "
-                        "chain+transitive edge, search E=2 chain; six load levels 25..150; log-normal delays "
-                        "calibrated on the reference traces)",
-            "services_per_gpu": int(hb.n_problems), "in_spans_per_service": args.n_in,
-            "spans_per_gpu": int(n_spans), "spans_total": int(n_spans * world),
-            "sharding": f"by service, {world} rank(s), no data-path collective",
-            "l2": "inputs+outputs per step (>1 GB) exceed the 126 MB L2; no explicit flush",
-            "passes": 2, "refit": "device GMM (BIC over 1..5 components) between passes"}
 
 
 class ClockSampler:
@@ -83,11 +95,11 @@ class ClockSampler:
                 pass
             self.stop.wait(0.05)
 
-    def __enter__(self):
+    def start(self):
         self.th.start()
         return self
 
-    def __exit__(self, *a):
+    def finish(self):
         self.stop.set()
         self.th.join(timeout=6)
 
@@ -104,32 +116,278 @@ class ClockSampler:
 
 def accuracy(assign, truth, hb):
     """Fraction of incoming spans whose children are all assigned correctly (AccuracyForService,
-    helpers/utils.py:62-79, on index arrays)."""
+    helpers/utils.py:62-79, on index arrays), computed on the device."""
     import torch
     ok = (assign == truth)
     tot, good = 0, 0
     E_of = np.diff(hb.prob_ep_off)
     n_of = np.diff(hb.prob_in_off)
     for E in np.unique(E_of):
-        sel = np.flatnonzero(E_of == E)
-        n = int(n_of[sel[0]])
-        if not np.all(n_of[sel] == n):
-            continue
-        offs = torch.as_tensor(hb.prob_tuple_off[sel], device=ok.device)
-        idx = offs[:, None] + torch.arange(E * n, device=ok.device)[None, :]
-        good += int(ok[idx].reshape(len(sel), E, n).all(dim=1).sum().item())
-        tot += len(sel) * n
+        for n in np.unique(n_of[E_of == E]):
+            sel = np.flatnonzero((E_of == E) & (n_of == n))
+            offs = torch.as_tensor(hb.prob_tuple_off[sel], device=ok.device)
+            idx = offs[:, None] + torch.arange(int(E) * int(n), device=ok.device)[None, :]
+            good += int(ok[idx].reshape(len(sel), int(E), int(n)).all(dim=1).sum().item())
+            tot += len(sel) * int(n)
     return good / max(tot, 1)
+
+
+def physical_cores():
+    """One hardware thread per physical core, from the kernel's topology files (sched affinity aware)."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return list(range(os.cpu_count() or 1))
+    seen, pick = set(), []
+    for c in allowed:
+        try:
+            sib = open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list").read().strip()
+        except OSError:
+            sib = str(c)
+        if sib not in seen:
+            seen.add(sib)
+            pick.append(c)
+    return pick or allowed
+
+
+def run_oracle_pinned(hb, seed, want_topk=True):
+    """The CPU port on one thread per physical core (pinned): oversubscribed hyper-threads made the
+    round-1 CPU arm swing 4.5x between hosts."""
+    from oracle import tw_oracle
+    cores = physical_cores()
+    old = None
+    try:
+        old = os.sched_getaffinity(0)
+        os.sched_setaffinity(0, cores)
+    except (AttributeError, OSError):
+        pass
+    try:
+        t0 = time.perf_counter()
+        res = tw_oracle.find_assignments(hb, seed, len(cores), want_topk=want_topk)
+        dt = time.perf_counter() - t0
+    finally:
+        if old is not None:
+            try:
+                os.sched_setaffinity(0, old)
+            except OSError:
+                pass
+    return res, dt, len(cores)
+
+
+def sample_blocks(blocks, per):
+    from traceweaver_b200.batch import ServiceBlock
+    out = []
+    for b in blocks:
+        k = min(per, b.in_start.shape[0])
+        out.append(ServiceBlock(in_start=b.in_start[:k], in_end=b.in_end[:k], out_start=[o[:k] for o in b.out_start],
+                                out_end=[o[:k] for o in b.out_end], preds=b.preds, truth=b.truth[:, :k], name=b.name))
+    return out
+
+
+def cpu_baseline(blocks, gpu_assign, n_services_sample, seed):
+    """oracle/ on the first services of every block (same inputs) + parity of the engine on them."""
+    from traceweaver_b200.batch import build_batch_from_blocks
+    per = max(1, n_services_sample // len(blocks))
+    sample = sample_blocks(blocks, per)
+    shb = build_batch_from_blocks(sample)
+    n_spans = int(sum(s.in_start.size * (1 + len(s.out_start)) for s in sample))
+    res, dt, cores = run_oracle_pinned(shb, seed)
+    same, pos, cum = True, 0, 0
+    for b, s in zip(blocks, sample):
+        S, n = b.in_start.shape
+        E = len(b.out_start)
+        k = s.in_start.shape[0]
+        same = same and bool(np.array_equal(gpu_assign[cum:cum + k * n * E], res["assign"][pos:pos + k * n * E]))
+        cum += S * n * E
+        pos += k * n * E
+    return {"value": n_spans / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {per} services of each of the {len(blocks)} blocks ({shb.n_problems} services, "
+                      f"{n_spans} spans), {dt:.1f} s wall, one pinned thread per physical core",
+            "engine_equals_oracle_on_sample": same}
+
+
+def measure(args, blocks, hb, dev_index, steps, warmup, gather=None, rank=0, world=1, want_cpu=True,
+            clock=False, cpu_sample=None):
+    """All legs for one service list on this rank.  Returns a dict of raw measurements."""
+    import torch
+    import torch.distributed as dist
+    from traceweaver_b200 import synth
+    from traceweaver_b200.engine import Engine
+    from traceweaver_b200.predictor import solve_bound
+    from traceweaver_b200.api import BatchSolver
+
+    dev = torch.device("cuda", dev_index)
+    n_spans = synth.span_count(blocks)
+    truth = torch.from_numpy(synth.truth_assign(blocks)).to(dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step(eng):
+        res = solve_bound(eng, seed_select=args.seed)
+        if gather is not None:
+            res["gathered"] = gather(res["assign"], rank)       # the data path's one collective
+        return res
+
+    # ---- leg 1: inputs resident in HBM
+    eng = Engine(dev_index)
+    eng.bind(hb)
+    for _ in range(warmup):
+        res = step(eng)
+    barrier()
+    l0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(dev_index).start() if clock else None
+    ev0.record()
+    for _ in range(steps):
+        res = step(eng)
+    ev1.record()
+    barrier()
+    if sampler:
+        sampler.finish()
+    resident_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = eng.launch_count() - l0
+    acc = accuracy(res["assign"], truth, hb)
+    unassigned = int(res["counters"][:, 1].sum().item())
+    gather_ok = None
+    if gather is not None:
+        mine = gather.shards(res["gathered"])[rank]
+        gather_ok = bool(torch.equal(mine, res["assign"]))
+
+    # ---- roofline of the scoring kernel (GMM pass: the final top-K lists), CUDA events on our stream
+    p1 = res["params_pass1"]
+    reps = 5
+    top = eng.score(p1, out=dict(cut=res["cut"]), keep_windows=True)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        eng.score(p1, out=top, keep_windows=True)
+    b.record()
+    torch.cuda.synchronize()
+    score_ms = a.elapsed_time(b) / reps
+    E_of = np.diff(hb.prob_ep_off).astype(np.int64)
+    n_of = np.diff(hb.prob_in_off).astype(np.int64)
+    alg_bytes = int(np.sum(n_of * (16 * (1 + E_of) + 5 * (8 + 4 * E_of))))     # SURVEY.md §8(d)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (score_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        per = json.load(open(os.path.join(ROOT, "profiles", "score_traffic.json"))).get("dram_bytes_per_in_span")
+        traffic = int(per * int(n_of.sum())) if per else None   # ncu capture scaled to this launch's in-spans
+    except Exception:
+        pass
+    roofline = {"kernel": "k_score3<E> (one launch per E present; + sequential redo of flagged tiles): GMM pass, "
+                          "final top-K", "bound": "hbm",
+                "achieved": round(achieved, 2), "peak": peak,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
+                "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": traffic,
+                "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": round(score_ms, 4),
+                "tiles_redone_sequentially": eng.redo_tile_count(), "tiles": eng.tile_count()}
+    eng.close()
+
+    # ---- leg 2: end to end through the public batch API, host buffers in and out.  The caller's
+    # arrays are rewritten in place before every step (time shift: same problem, new bytes).
+    solver = BatchSolver(device=dev_index, seed_select=args.seed)
+    for _ in range(max(warmup, 1)):
+        out = solver.solve(hb)
+    barrier()
+    e2e_ms_sum = 0.0
+    span_arrays = ("in_start", "in_end", "out_start", "out_end")
+    for k in range(steps):
+        for name in span_arrays:
+            hb.arrays[name] += 1                      # untimed: the caller refills its buffers
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        out = solver.solve(hb)
+        if gather is not None:
+            gather(torch.from_numpy(out["assign"]).to(dev, non_blocking=True), rank)
+        e1.record()
+        barrier()
+        e2e_ms_sum += max_over_ranks(e0.elapsed_time(e1))
+    e2e = {"ms": e2e_ms_sum, "h2d": solver.h2d_bytes, "d2h": solver.d2h_bytes, "chunks": solver.last_chunks}
+    gpu_assign = np.array(out["assign"])
+    for name in span_arrays:
+        hb.arrays[name] -= steps
+    solver.close()
+
+    cpu = None
+    if want_cpu and rank == 0 and world == 1:
+        cpu = cpu_baseline(blocks, gpu_assign, cpu_sample or args.cpu_sample, args.seed)
+    return dict(n_spans=n_spans, resident_ms=resident_ms, launches=launches, accuracy=acc, unassigned=unassigned,
+                roofline=roofline, e2e=e2e, cpu=cpu, gather_ok=gather_ok,
+                clocks=sampler.summary() if sampler else None)
+
+
+def shipped_directories(dev_index):
+    """BASELINE configs[1]/[2] as shipped: the service problems of the reference's Jaeger directories
+    (tests/golden holds the arrays the reference's loader produced), each directory solved as one
+    batch through the public API, compared with the reference's own assignments."""
+    import glob
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from golden_util import Golden, GOLDEN_DIR
+    from traceweaver_b200.api import BatchSolver
+    from traceweaver_b200.batch import build_batch
+    files = sorted(glob.glob(os.path.join(GOLDEN_DIR, "*__*.npz")))
+    if not files:
+        return None
+    by_dir = {}
+    for f in files:
+        by_dir.setdefault(os.path.basename(f).split("__")[0], []).append(Golden(f))
+    solver = BatchSolver(device=dev_index, seed_select=10)
+    rows, tot_spans, tot_ms, equal_all, ref_s = [], 0, 0.0, True, 0.0
+    for name, gs in sorted(by_dir.items()):
+        probs = [g.problem() for g in gs]
+        hb = build_batch(probs)
+        spans = int(sum(p.n_in + sum(len(o) for o in p.out_start) for p in probs))
+        solver.solve(hb)
+        torch.cuda.synchronize()
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            out = solver.solve(hb)
+        ms = (time.perf_counter() - t0) * 1e3 / reps
+        equal = True
+        for p, g in enumerate(gs):
+            t0_, t1_ = int(hb.prob_tuple_off[p]), int(hb.prob_tuple_off[p + 1])
+            equal = equal and bool(np.array_equal(out["assign"][t0_:t1_].reshape(g.E, -1), g.z["assign"]))
+        equal_all = equal_all and equal
+        ref_s += sum(float(g.meta.get("reference_seconds", 0.0)) for g in gs)
+        rows.append({"directory": name, "services": len(gs), "spans": spans, "ms": round(ms, 3),
+                     "assignments_equal_reference": equal})
+        tot_spans += spans
+        tot_ms += ms
+    solver.close()
+    return {"workload": "shipped Jaeger directories (hotel / media / nodejs problems as the reference's loader built "
+                        "them), one directory per call through BatchSolver, wall clock incl. staging, H2D and D2H",
+            "directories": len(rows), "spans": tot_spans, "ms_total": round(tot_ms, 2),
+            "e2e_value": tot_spans / (tot_ms * 1e-3), "unit": UNIT,
+            "assignments_equal_reference": equal_all,
+            "reference_python_seconds_when_minted": round(ref_s, 1), "per_directory": rows}
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from traceweaver_b200 import synth
+    from traceweaver_b200 import shard
     from traceweaver_b200.batch import build_batch_from_blocks
-    from traceweaver_b200.engine import Engine
-    from traceweaver_b200.predictor import solve_bound
-    from traceweaver_b200.api import BatchSolver
 
     rank, local_rank, world = dist_env()
     torch.cuda.set_device(local_rank)
@@ -150,188 +408,121 @@ def run_ours(args):
             os.close(saved_stdout)
     dev = torch.device("cuda", local_rank)
 
-    # ---- this rank's shard of the stream (synthetic, seeded; generation is not timed)
-    from traceweaver_b200 import shard
-    blocks = synth.hotel_stream(args.services, args.n_in, seed=shard.shard_seed(args.seed, rank))
+    # ---- ONE global service list, partitioned by span count; this rank generates only its slice
+    if args.scaling == "weak":
+        n_services = args.services * world
+    else:
+        probe = shard.stream_spec(args.workload, 1200, args.n_in, args.seed)
+        n_services = int(round(args.spans / shard.spec_span_counts(probe).mean()))
+    specs = shard.stream_spec(args.workload, n_services, args.n_in, args.seed)
+    span_counts = shard.spec_span_counts(specs)
+    bounds = shard.partition_by_spans(span_counts, world)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    blocks = shard.generate_slice(specs, lo, hi)
     hb = build_batch_from_blocks(blocks)
-    n_spans = synth.span_count(blocks)
-    truth = torch.from_numpy(synth.truth_assign(blocks)).to(dev)
+    total_spans = int(span_counts.sum())
+    gather = shard.AssignGather(shard.spec_tuple_counts(specs), bounds, dev) if world > 1 else None
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    m = measure(args, blocks, hb, local_rank, args.steps, args.warmup, gather=gather, rank=rank, world=world,
+                clock=True)
 
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- leg 1: inputs resident in HBM
-    eng = Engine(local_rank)
-    eng.bind(hb)
-    for _ in range(args.warmup):
-        res = solve_bound(eng, seed_select=args.seed)
-    barrier()
-    l0 = eng.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
-        ev0.record()
-        for _ in range(args.steps):
-            res = solve_bound(eng, seed_select=args.seed)
-        ev1.record()
-        barrier()
-    resident_ms = max_over_ranks(ev0.elapsed_time(ev1))
-    launches = eng.launch_count() - l0
-    acc = accuracy(res["assign"], truth, hb)
-    unassigned = int(res["counters"][:, 1].sum().item())
-
-    # ---- roofline of the scoring kernel (GMM pass: the final top-K lists), CUDA events on our stream
-    p1 = res["params_pass1"]
-    reps = 5
-    eng.score(p1)
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(reps):
-        eng.score(p1)
-    b.record()
-    torch.cuda.synchronize()
-    score_ms = a.elapsed_time(b) / reps
-    E_of = np.diff(hb.prob_ep_off).astype(np.int64)
-    n_of = np.diff(hb.prob_in_off).astype(np.int64)
-    alg_bytes = int(np.sum(n_of * (16 * (1 + E_of) + 5 * (8 + 4 * E_of))))
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = alg_bytes / (score_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        per = json.load(open(os.path.join(ROOT, "profiles", "score_traffic.json"))).get("dram_bytes_per_in_span")
-        traffic = int(per * int(n_of.sum())) if per else None   # ncu capture scaled to this launch's in-spans
-    except Exception:
-        pass
-    roofline = {"kernel": "k_score2<128> (+ k_score<32,64> overflow redo): GMM pass, final top-K", "bound": "hbm",
-                "achieved": round(achieved, 2),
-                "peak": peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
-                "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": traffic,
-                "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": round(score_ms, 4)}
-    eng.close()
-
-    # ---- leg 2: end to end through the public batch API, host buffers in and out
-    solver = BatchSolver(device=local_rank, seed_select=args.seed)
-    for _ in range(args.warmup):
-        out = solver.solve(hb)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        out = solver.solve(hb)
-    e1.record()
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
-    h2d, d2h = solver.h2d_bytes, solver.d2h_bytes
-    chunks = len(solver._plan[1]) if solver._plan else 1
-    solver.close()
-
-    # ---- CPU baseline (rank 0, N=1 only): the C restatement on a bounded sample of the same services
-    cpu = None
-    if rank == 0 and world == 1:
-        cpu = cpu_baseline(args, blocks, out, hb)
+    extra = []
+    if rank == 0 and world == 1 and not args.no_extra:
+        # the other BASELINE shapes: smaller lists and fewer steps so the default run stays within minutes
+        for wl, ns, n_in in (("media", 2046, 1000), ("alibaba", 2016, 1250)):
+            if wl == args.workload:
+                continue
+            try:
+                sp = shard.stream_spec(wl, ns, n_in, args.seed)
+                bl = shard.generate_slice(sp, 0, ns)
+                h2 = build_batch_from_blocks(bl)
+                r = measure(args, bl, h2, local_rank, 3, 3, want_cpu=True, cpu_sample=108)
+                extra.append({"workload": WORKLOAD_TEXT[wl], "services": h2.n_problems, "spans": r["n_spans"],
+                              "value": r["n_spans"] * 3 / (r["resident_ms"] * 1e-3), "unit": UNIT,
+                              "ms_per_step": r["resident_ms"] / 3,
+                              "e2e_value": r["n_spans"] * 3 / (r["e2e"]["ms"] * 1e-3),
+                              "accuracy": r["accuracy"], "unassigned": r["unassigned"], "roofline": r["roofline"],
+                              "cpu_baseline": r["cpu"],
+                              "engine_equals_oracle_on_sample": r["cpu"]["engine_equals_oracle_on_sample"]})
+            except Exception as ex:       # an extra leg must not take the headline line down with it
+                extra.append({"workload": WORKLOAD_TEXT[wl], "error": repr(ex)[:300]})
+        try:
+            sd = shipped_directories(local_rank)
+            if sd:
+                extra.append(sd)
+        except Exception as ex:
+            extra.append({"workload": "shipped Jaeger directories", "error": repr(ex)[:300]})
 
     if rank == 0:
-        total = n_spans * world
+        K = args.steps
+        sharding = (f"one list of {n_services} services partitioned by span count over {world} rank(s); "
+                    + ("one NCCL all_gather_into_tensor of the assignment arrays per step, inside the timed region"
+                       if world > 1 else "single rank: no collective"))
+        cfg = {"workload": WORKLOAD_TEXT[args.workload], "services_total": int(n_services),
+               "services_this_rank": int(hb.n_problems), "in_spans_per_service": args.n_in,
+               "spans_total": total_spans, "sharding": sharding,
+               "l2": "inputs+outputs per step (>1 GB) exceed the 126 MB L2; no explicit flush",
+               "passes": 2, "refit": "device GMM (BIC over 1..5 components) between passes"}
         line = {
-            "metric": METRIC, "value": total * args.steps / (resident_ms * 1e-3), "unit": UNIT,
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": resident_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": total_spans * K / (m["resident_ms"] * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": m["resident_ms"] / K, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "int64 timestamps, f64 log-likelihoods", "data": "synthetic",
-            "config": workload_config(args, world, hb, n_spans),
-            "accuracy": {"assignment_accuracy": acc, "unassigned": unassigned,
-                         "note": "fraction of incoming spans with all children correct vs generator ground truth"},
-            "e2e": {"value": total * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "config": cfg,
+            "accuracy": {"assignment_accuracy": m["accuracy"], "unassigned": m["unassigned"],
+                         "note": "fraction of incoming spans with all children correct vs generator ground truth "
+                                 "(rank 0's services)"},
+            "e2e": {"value": total_spans * K / (m["e2e"]["ms"] * 1e-3), "unit": UNIT,
+                    "ms_per_step": m["e2e"]["ms"] / K,
+                    "h2d_bytes_per_step": m["e2e"]["h2d"], "d2h_bytes_per_step": m["e2e"]["d2h"],
                     "api": "traceweaver_b200.api.BatchSolver.solve(host batch) -> host arrays",
-                    "overlap": f"{chunks} service groups round-robin on 2 streams (copies overlap kernels)"},
-            "gpu_launches": int(launches),
-            "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "impl": "ours",
+                    "host_staging": "caller arrays rewritten in place before every step; solve() memcpys them into "
+                                    "pinned staging every call (inside the timed region)",
+                    "overlap": f"{m['e2e']['chunks']} service groups round-robin on 2 streams (copies overlap kernels)"},
+            "gpu_launches": int(m["launches"]),
+            "collective": None if gather is None else {
+                "op": "all_gather_into_tensor(int32 assign)",
+                "bytes_received_per_rank_per_step": gather.bytes_received_per_rank,
+                "own_shard_round_trips": m["gather_ok"]},
+            "clocks": m["clocks"], "roofline": m["roofline"], "cpu_baseline": m["cpu"], "impl": "ours",
+            "extra_workloads": extra,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(args, blocks, gpu_out, hb):
-    """oracle/ on the first `cpu_sample` services of every block (same inputs), all host threads."""
-    from oracle import tw_oracle
-    from traceweaver_b200.batch import build_batch_from_blocks, ServiceBlock
-    per = max(1, args.cpu_sample // len(blocks))
-    sample = [ServiceBlock(in_start=b.in_start[:per], in_end=b.in_end[:per], out_start=[o[:per] for o in b.out_start],
-                           out_end=[o[:per] for o in b.out_end], preds=b.preds, truth=b.truth[:, :per], name=b.name)
-              for b in blocks]
-    shb = build_batch_from_blocks(sample)
-    n_spans = int(sum(s.in_start.size * (1 + len(s.out_start)) for s in sample))
-    cores = os.cpu_count() or 1
-    tw_oracle.build()
-    t0 = time.perf_counter()
-    res = tw_oracle.find_assignments(shb, args.seed, cores, want_topk=True)
-    dt = time.perf_counter() - t0
-    # parity on the sample: the engine's assignments for these services must equal the oracle's
-    same = True
-    pos = 0
-    gpu_assign = gpu_out["assign"]
-    cum = 0
-    for b, s in zip(blocks, sample):
-        S, n = b.in_start.shape
-        E = len(b.out_start)
-        g = gpu_assign[cum:cum + per * n * E]
-        o = res["assign"][pos:pos + per * n * E]
-        same = same and bool(np.array_equal(g, o))
-        cum += S * n * E
-        pos += per * n * E
-    return {"value": n_spans / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"first {per} services of each of the {len(blocks)} blocks ({shb.n_problems} services, "
-                      f"{n_spans} spans), {dt:.1f} s wall",
-            "engine_equals_oracle_on_sample": same}
-
-
 def run_reference(args):
     """CPU arm: the reference's algorithm (oracle/ C port; the Python reference cannot travel to the
-    GPU box and needs Gurobi) with all host threads, each step = a bounded sample of the workload."""
+    GPU box and needs Gurobi), one pinned thread per physical core, each step = a bounded sample of
+    the workload sized for seconds of CPU work."""
     rank, _, world = dist_env()
     if rank != 0:
         return
     from oracle import tw_oracle
-    from traceweaver_b200 import synth
+    from traceweaver_b200 import shard, synth
     from traceweaver_b200.batch import build_batch_from_blocks
     tw_oracle.build()
-    cores = os.cpu_count() or 1
-    per_block = max(1, args.cpu_sample // 12)
-    blocks = synth.hotel_stream(per_block * 12, args.n_in, seed=args.seed)
+    cores = len(physical_cores())
+    n_services = max(args.cpu_sample, 24 * cores)
+    specs = shard.stream_spec(args.workload, n_services, args.n_in, args.seed, block_services=max(1, n_services // 12))
+    blocks = shard.generate_slice(specs, 0, n_services)
     hb = build_batch_from_blocks(blocks)
     n_spans = synth.span_count(blocks)
     for _ in range(min(args.warmup, 1)):
-        tw_oracle.find_assignments(hb, args.seed, cores, want_topk=True)
-    t0 = time.perf_counter()
+        run_oracle_pinned(hb, args.seed)
+    dt = 0.0
     for _ in range(args.steps):
-        tw_oracle.find_assignments(hb, args.seed, cores, want_topk=True)
-    dt = time.perf_counter() - t0
+        dt += run_oracle_pinned(hb, args.seed)[1]
     v = n_spans * args.steps / dt
-    cfg = workload_config(args, world, hb, n_spans)
-    cfg["services_per_gpu"] = None
-    cfg["sample"] = f"{hb.n_problems} services ({n_spans} spans) per step on {cores} host threads"
+    sample = f"{hb.n_problems} services ({n_spans} spans) per step on {cores} pinned threads (one per physical core)"
+    cfg = {"workload": WORKLOAD_TEXT[args.workload], "services_total": None, "in_spans_per_service": args.n_in,
+           "sample": sample, "passes": 2, "refit": "C restatement of the sklearn GMM refit between passes"}
     print(json.dumps({
         "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "int64 timestamps, f64 log-likelihoods", "data": "synthetic", "config": cfg, "impl": "reference",
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": cfg["sample"]},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TW_ABI_VERSION 1
+#define TW_ABI_VERSION 2
 
 /* Algorithm constants hard-coded by the reference. */
 #define TW_MAX_E 8             /* engine limit on out-eps per service (shipped data: <= 4)      */
@@ -127,7 +127,16 @@ typedef struct tw_score_out {
   int32_t* used_lo;       /* [prob_tuple_off[P]]   used_lo[tuple_off[p] + i*E + e]                 */
   uint32_t* used_bits;    /* [2 * prob_tuple_off[P]]  two words per (in-span, ep)                  */
   uint8_t* used_wide;     /* [n_in_total] 1 = the in-span's candidates exceed 64 per ep (no map)   */
+  uint32_t flags;         /* TW_SCORE_* bits                                                       */
+  uint32_t reserved0;
 } tw_score_out;
+
+/* tw_score_out.flags.  The windows (cut, n_feasible, used maps) depend on the span arrays only
+ * (V3:1115 builds them once, before any deletion, and both iterations reuse them).  A second
+ * tw_score_topk on the same bound batch — the final top-K with the refitted parameters — may set
+ * TW_SCORE_KEEP_WINDOWS: cut and used_* are then neither read nor written (the arrays the first
+ * call filled stay valid), only topk_* and n_feasible are produced.                              */
+#define TW_SCORE_KEEP_WINDOWS 1u
 
 typedef struct tw_engine tw_engine;   /* opaque: bound batch, device scratch, error string       */
 
@@ -163,6 +172,11 @@ int tw_prepare(tw_engine* eng, void* stream);
 /* Blocks until `stream` is idle and returns the sticky device-side status of the kernels
  * launched since the last call (TW_OK, TW_ERR_MWIS_LIMIT, TW_ERR_RANGE_LIMIT, ...). */
 int tw_engine_status(tw_engine* eng, void* stream);
+
+/* Scoring tiles of the bound batch (128 in-spans each) and how many of them the last tw_score_topk
+ * handed to the sequential kernel (candidate ranges wider than the maps, score ties, NaN scores).
+ * Blocks until `stream` is idle.  Either pointer may be NULL. */
+int tw_engine_tile_stats(tw_engine* eng, int64_t* n_tiles, int64_t* n_redone, void* stream);
 
 /* Number of kernels this engine has launched since creation (bench.py's gpu_launches). */
 int64_t tw_engine_launch_count(const tw_engine* eng);

@@ -41,7 +41,7 @@ def test_struct_layout_matches_header(lib):
     assert C.sizeof(_abi.TwBatch) == 16 + 16 + 11 * 8
     assert C.sizeof(_abi.TwParams) == 8 + 3 * 8
     assert C.sizeof(_abi.TwPassOut) == 7 * 8
-    assert C.sizeof(_abi.TwScoreOut) == 8 * 8
+    assert C.sizeof(_abi.TwScoreOut) == 9 * 8
 
 
 def test_host_validation(lib):

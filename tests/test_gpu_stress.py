@@ -140,7 +140,22 @@ def test_chunked_solver_matches_single_pass():
         got = many.solve(hb)
         for k in ref:
             assert np.array_equal(got[k], ref[k]), k
-    assert len(many._plan[1]) == 3
+    assert many.last_chunks == 3
+    # the caller refills its buffers in place: the next call must see the new contents
+    hb2 = build_batch_from_blocks([synth.make_block("hotel_frontend", 7, 300, 150.0, seed=15),
+                                   synth.make_block("hotel_search", 6, 200, 150.0, seed=16)])
+    one = BatchSolver(device=0, seed_select=10, chunks=1)
+    ref2 = {k: v.copy() for k, v in one.solve(hb2).items()}
+    one.close()
+    for name in ("in_start", "in_end", "out_start", "out_end"):
+        hb.arrays[name][:] = hb2.arrays[name]
+    got2 = many.solve(hb)
+    for k in ref2:
+        assert np.array_equal(got2[k], ref2[k]), k
+    assert not np.array_equal(ref["assign"], ref2["assign"])
+    # results of the previous call are still intact (two result sets alternate)
+    for k in ref:
+        assert np.array_equal(got[k], ref[k]), k
     many.close()
 
 

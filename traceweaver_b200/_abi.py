@@ -4,7 +4,8 @@ Field order and widths must match the header exactly; tests/test_abi.py checks s
 against values compiled from the header."""
 import ctypes as C
 
-TW_ABI_VERSION = 1
+TW_ABI_VERSION = 2
+TW_SCORE_KEEP_WINDOWS = 1
 TW_MAX_E = 8
 TW_K = 5
 TW_MAX_WINDOW = 30
@@ -49,7 +50,8 @@ class TwPassOut(C.Structure):
 
 class TwScoreOut(C.Structure):
     _fields_ = [("topk_score", P), ("topk_idx", P), ("topk_cnt", P), ("n_feasible", P), ("cut", P),
-                ("used_lo", P), ("used_bits", P), ("used_wide", P)]
+                ("used_lo", P), ("used_bits", P), ("used_wide", P), ("flags", C.c_uint32),
+                ("reserved0", C.c_uint32)]
 
 
 class TwError(RuntimeError):

@@ -23,6 +23,7 @@ SYMBOLS = {
     "tw_prepare": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tw_engine_status": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tw_engine_launch_count": (C.c_int64, [C.c_void_p]),
+    "tw_engine_tile_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]),
     "tw_params_pass0": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tw_score_topk": (C.c_int, [C.c_void_p, C.POINTER(_abi.TwParams), C.POINTER(_abi.TwScoreOut), C.c_void_p]),
     "tw_stitch": (C.c_int, [C.c_void_p, C.POINTER(_abi.TwParams), C.c_void_p, C.POINTER(_abi.TwScoreOut),

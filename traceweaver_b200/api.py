@@ -10,8 +10,14 @@
 
 This is `TraceWeaverV3.FindAssignments` (traceweaver_v3.py:1087-1229) for every service of the
 batch in one launch sequence; `predictor.TraceWeaverV3` is the same path behind the reference's
-one-service-at-a-time plugin signature.  Every step copies the span arrays host->device from
-pinned memory and the results device->host; nothing is cached across calls except device scratch.
+one-service-at-a-time plugin signature.  Every call copies the caller's span arrays into page-locked
+staging buffers (a host memcpy, every call: the caller may refill its buffers in place), sends them
+host->device, and brings the results device->host; nothing about the batch CONTENTS is cached across
+calls — only buffers (device scratch, staging, result buffers) are re-used.
+
+Result lifetime: the returned arrays are views of page-locked result buffers owned by the solver.
+Two sets alternate, so the arrays of a call stay valid until the SECOND next call of `solve()`;
+copy them if you keep them longer (`np.array(out["assign"])`).
 """
 import numpy as np
 import torch
@@ -46,8 +52,9 @@ class BatchSolver:
         self._streams = None
         self._copy_stream = None
         self._pinned_in = {}
-        self._pinned_out = {}
-        self._plan = None
+        self._pinned_out = [{}, {}]
+        self._flip = 0
+        self.last_chunks = 1
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -55,46 +62,47 @@ class BatchSolver:
         for e in self._engines:
             e.close()
 
-    def _pin(self, name, a):
-        """The caller's host buffer, page-locked (re-used when the same array comes back)."""
-        key = (a.__array_interface__["data"][0], a.nbytes)
+    def _stage(self, name, a):
+        """Copy the caller's host array into a page-locked staging buffer (allocated once per
+        shape; the copy happens on EVERY call — the buffer's address says nothing about its contents)."""
+        src = a.view(np.int32) if a.dtype == np.uint32 else a
+        src = torch.from_numpy(np.ascontiguousarray(src))
         t = self._pinned_in.get(name)
-        if t is None or t[0] != key:
-            src = a.view(np.int32) if a.dtype == np.uint32 else a
-            t = (key, torch.from_numpy(np.ascontiguousarray(src)).pin_memory())
+        if t is None or t.shape != src.shape or t.dtype != src.dtype:
+            t = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
             self._pinned_in[name] = t
-        return t[1]
+        t.copy_(src)
+        return t
 
     def _out_buf(self, name, n, dtype, cols=None):
         shape = (n,) if cols is None else (n, cols)
-        buf = self._pinned_out.get(name)
+        bufs = self._pinned_out[self._flip]
+        buf = bufs.get(name)
         if buf is None or tuple(buf.shape) != shape or buf.dtype != dtype:
             buf = torch.empty(shape, dtype=dtype, pin_memory=True)
-            self._pinned_out[name] = buf
+            bufs[name] = buf
         return buf
 
     def _chunk_plan(self, hb: HostBatch):
-        """[(lo, hi, sub-batch)] — cached per batch object so that the pinned staging is re-used."""
+        """[(lo, hi, sub-batch)]: recomputed every call (O(P) descriptor arithmetic, span arrays are views)."""
         n_in = int(hb.prob_in_off[-1])
         C = self.chunks if n_in >= self.MIN_CHUNK_IN_SPANS else 1
         C = min(C, hb.n_problems)
-        key = (id(hb), hb.in_start.__array_interface__["data"][0], C)
-        if self._plan is None or self._plan[0] != key:
-            if C == 1:
-                plan = [(0, hb.n_problems, hb)]
-            else:
-                # a small first group (its host->device copy is the only one nothing can hide), the
-                # rest in equal in-span counts
-                first = self.FIRST_GROUP_FRACTION if C == 2 else 1.0 / C
-                fr = first + (1.0 - first) * np.arange(0, C - 1) / max(C - 1, 1)
-                cuts = np.searchsorted(hb.prob_in_off, fr * n_in, side="left")
-                edges = sorted(set([0, hb.n_problems] + [int(c) for c in cuts if 0 < c < hb.n_problems]))
-                plan = [(lo, hi, hb.slice(lo, hi)) for lo, hi in zip(edges[:-1], edges[1:])]
-            self._plan = (key, plan)
-        return self._plan[1]
+        if C == 1:
+            return [(0, hb.n_problems, hb)]
+        # a first group (its host->device copy is the only one nothing can hide), the rest in equal
+        # in-span counts
+        first = self.FIRST_GROUP_FRACTION if C == 2 else 1.0 / C
+        fr = first + (1.0 - first) * np.arange(0, C - 1) / max(C - 1, 1)
+        cuts = np.searchsorted(hb.prob_in_off, fr * n_in, side="left")
+        edges = sorted(set([0, hb.n_problems] + [int(c) for c in cuts if 0 < c < hb.n_problems]))
+        return [(lo, hi, hb.slice(lo, hi)) for lo, hi in zip(edges[:-1], edges[1:])]
 
-    def solve(self, hb: HostBatch, truth_assign=None, term_order=None):
+    def solve(self, hb: HostBatch, truth_assign=None, term_order=None, want_scores=False):
+        """want_scores: also return out["topk_score"] (float64 [sum n_in, 5]; the reference's 6-tuple
+        carries the top-K ids only, traceweaver_v3.py:1229, so the scores stay on the device by default)."""
         dev = self.engine.device
+        self._flip ^= 1
         single = truth_assign is not None or term_order is not None
         plan = [(0, hb.n_problems, hb)] if single else self._chunk_plan(hb)
         if len(plan) > 1 and self._streams is None:
@@ -110,6 +118,9 @@ class BatchSolver:
             n_cand=self._out_buf("n_cand", n_in, torch.int32),
             counters=self._out_buf("counters", hb.n_problems, torch.int32, 4),
             mis_rank=self._out_buf("mis_rank", n_in, torch.int8))
+        if want_scores:
+            out["topk_score"] = self._out_buf("topk_score", n_in, torch.float64, _abi.TW_K)
+        self.last_chunks = len(plan)
         h2d = d2h = 0
         main = torch.cuda.current_stream(dev)
         used = []
@@ -121,7 +132,7 @@ class BatchSolver:
             with torch.cuda.stream(stream):
                 d = {}
                 for name, a in sub.arrays.items():
-                    p = self._pin((c, name), a)
+                    p = self._stage((c, name), a)
                     d[name] = p.to(dev, non_blocking=True)        # H2D inside the caller's timed region
                     h2d += p.numel() * p.element_size()
                 eng.bind(sub, device_arrays=d)
@@ -141,14 +152,18 @@ class BatchSolver:
                     ev.record(stream)
                     self._copy_stream.wait_event(ev)
                     with torch.cuda.stream(self._copy_stream):
-                        for name, (b0, b1) in (("topk_idx", (_abi.TW_K * t0, _abi.TW_K * t1)), ("topk_cnt", (i0, i1))):
+                        names = [("topk_idx", (_abi.TW_K * t0, _abi.TW_K * t1)), ("topk_cnt", (i0, i1))]
+                        if want_scores:
+                            names.append(("topk_score", (i0, i1)))
+                        for name, (b0, b1) in names:
                             t = top[name]
                             t.record_stream(self._copy_stream)
                             out[name][b0:b1].copy_(t, non_blocking=True)
 
                 res = solve_bound(eng, seed_select=self.seed_select, truth_assign=ta, term_order=to, check=False,
                                   after_score=copy_topk)
-                d2h += sum(res[k].numel() * res[k].element_size() for k in ("topk_idx", "topk_cnt"))
+                d2h += sum(res[k].numel() * res[k].element_size()
+                           for k in ("topk_idx", "topk_cnt") + (("topk_score",) if want_scores else ()))
                 for name, (b0, b1) in (("assign", (t0, t1)), ("n_cand", (i0, i1)), ("counters", (lo, hi)),
                                        ("mis_rank", (i0, i1))):
                     t = res[name]

@@ -38,14 +38,21 @@ struct tw_engine {
   std::vector<int64_t> prob_in_off;
   std::vector<int32_t> prob_ep_off;
   int max_seg = 0;
+  int64_t dev_n_tuple = 0;
   // device scratch (owned, grow-only: re-binding a batch of similar size allocates nothing)
   struct Slot { void* p = nullptr; size_t bytes = 0; };
   std::map<void*, Slot> slots;
   int32_t* prev_idx = nullptr;
-  int32_t* narrow_tiles = nullptr;   // [2*n]: prob, start
-  int32_t* wide_tiles = nullptr;     // [3*n]: prob, start, narrow index
-  int n_narrow = 0, n_wide = 0;
-  uint8_t* narrow_overflow = nullptr;
+  int32_t* score_tiles = nullptr;    // [2*n]: prob, start; grouped by the problem's E (class_off)
+  int32_t* tile_win = nullptr;       // [n][2*TW_MAX_E] candidate slice per ep (k_tile_meta)
+  int32_t* wide_tiles = nullptr;     // [4*n]: prob, start, scoring-tile index, length
+  int n_tiles = 0, n_wide = 0;
+  int class_off[TW_MAX_E + 1] = {0};
+  uint8_t* tile_overflow = nullptr;
+  bool windows_valid = false;        // cut / maps / overflow flags of this batch have been produced
+  int32_t* own_used_lo = nullptr;    // candidate maps when the caller does not ask for them
+  uint32_t* own_used_bits = nullptr;
+  uint8_t* own_used_wide = nullptr;
   uint32_t* taken = nullptr;
   size_t taken_words = 0;
   int* err_flag = nullptr;
@@ -187,31 +194,41 @@ int tw_engine_bind(tw_engine* eng, const tw_batch* dev, const tw_batch* h, void*
   const int P = h->n_problems;
   eng->prob_in_off.assign(h->prob_in_off, h->prob_in_off + P + 1);
   eng->prob_ep_off.assign(h->prob_ep_off, h->prob_ep_off + P + 1);
+  eng->dev_n_tuple = h->prob_tuple_off[P];
 
-  // ---- tile lists (a tile never crosses a problem; wide tiles subdivide narrow ones)
-  std::vector<int32_t> nt_prob, nt_start, wt_prob, wt_start, wt_narrow, bprob, bidx;
+  // ---- tile lists (a tile never crosses a problem; scoring tiles are grouped by E; wide tiles
+  // subdivide scoring tiles and carry their length)
+  std::vector<int32_t> nt_prob, nt_start, wt_prob, wt_start, wt_narrow, wt_len, bprob, bidx;
   const int wide_len = kWideThreads - 1;
   eng->max_seg = 0;
+  eng->windows_valid = false;
+  eng->class_off[0] = 0;
+  for (int Ec = 1; Ec <= TW_MAX_E; ++Ec) {
+    for (int p = 0; p < P; ++p) {
+      if (h->prob_ep_off[p + 1] - h->prob_ep_off[p] != Ec) continue;
+      int n = (int)(h->prob_in_off[p + 1] - h->prob_in_off[p]);
+      for (int i0 = 0; i0 < n; i0 += kS3Tile) {
+        int tile_id = (int)nt_prob.size();
+        nt_prob.push_back(p);
+        nt_start.push_back(i0);
+        int lim = i0 + kS3Tile < n ? i0 + kS3Tile : n;
+        for (int j0 = i0; j0 < lim; j0 += wide_len) {
+          wt_prob.push_back(p);
+          wt_start.push_back(j0);
+          wt_narrow.push_back(tile_id);
+          wt_len.push_back(lim - j0 < wide_len ? lim - j0 : wide_len);
+        }
+      }
+    }
+    eng->class_off[Ec] = (int)nt_prob.size();
+  }
   for (int p = 0; p < P; ++p) {
     int n = (int)(h->prob_in_off[p + 1] - h->prob_in_off[p]);
     if (n > eng->max_seg) eng->max_seg = n;
-    for (int i0 = 0; i0 < n; i0 += kScoreTile) {
-      int narrow_id = (int)nt_prob.size();
-      nt_prob.push_back(p);
-      nt_start.push_back(i0);
-      int lim = i0 + kScoreTile < n ? i0 + kScoreTile : n;
-      for (int j0 = i0; j0 < lim; j0 += wide_len) {
-        // wide tiles must not run past their narrow tile: tile_len is clamped in-kernel by n only,
-        // so sub-tiles are cut at narrow boundaries by listing them explicitly with their length
-        wt_prob.push_back(p);
-        wt_start.push_back(j0);
-        wt_narrow.push_back(narrow_id);
-      }
-    }
     int nb = (n + TW_PARAM_BATCH - 1) / TW_PARAM_BATCH;
     for (int q = 0; q < nb; ++q) { bprob.push_back(p); bidx.push_back(q); }
   }
-  eng->n_narrow = (int)nt_prob.size();
+  eng->n_tiles = (int)nt_prob.size();
   eng->n_wide = (int)wt_prob.size();
   eng->n_batches_total = (int)bprob.size();
   std::vector<int32_t> term_ep(h->n_term_total), ep_prob(h->n_ep_total);
@@ -222,12 +239,20 @@ int tw_engine_bind(tw_engine* eng, const tw_batch* dev, const tw_batch* h, void*
     }
 
   CU(eng->alloc(&eng->prev_idx, (size_t)h->n_in_total));
-  CU(eng->alloc(&eng->narrow_tiles, (size_t)eng->n_narrow * 2));
-  CU(eng->alloc(&eng->wide_tiles, (size_t)eng->n_wide * 3));
-  CU(eng->alloc(&eng->narrow_overflow, (size_t)eng->n_narrow));
+  CU(eng->alloc(&eng->score_tiles, (size_t)eng->n_tiles * 2));
+  CU(eng->alloc(&eng->tile_win, (size_t)eng->n_tiles * 2 * TW_MAX_E));
+  CU(eng->alloc(&eng->wide_tiles, (size_t)eng->n_wide * 4));
+  CU(eng->alloc(&eng->tile_overflow, (size_t)eng->n_tiles));
   eng->taken_words = (size_t)(h->n_out_total / 32) + (size_t)h->n_ep_total + 2;
   CU(eng->alloc(&eng->taken, eng->taken_words));
-  CU(eng->alloc(&eng->err_flag, 1));
+  {
+    // the device status word is sticky across re-binds (a caller that pipelines several batches
+    // through one engine reads it once at the end): cleared when first allocated and by
+    // tw_engine_status only
+    int* before = eng->err_flag;
+    CU(eng->alloc(&eng->err_flag, 1));
+    if (eng->err_flag != before) CU(cudaMemsetAsync(eng->err_flag, 0, sizeof(int), s));
+  }
   CU(eng->alloc(&eng->in_end_sorted, (size_t)h->n_in_total));
   CU(eng->alloc(&eng->out_end_sorted, (size_t)h->n_out_total));
   CU(eng->alloc(&eng->batch_prob, bprob.size()));
@@ -237,16 +262,16 @@ int tw_engine_bind(tw_engine* eng, const tw_batch* dev, const tw_batch* h, void*
   auto up = [&](void* dst, const std::vector<int32_t>& src) {
     return cudaMemcpyAsync(dst, src.data(), src.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s);
   };
-  CU(up(eng->narrow_tiles, nt_prob));
-  CU(up(eng->narrow_tiles + eng->n_narrow, nt_start));
+  CU(up(eng->score_tiles, nt_prob));
+  CU(up(eng->score_tiles + eng->n_tiles, nt_start));
   CU(up(eng->wide_tiles, wt_prob));
   CU(up(eng->wide_tiles + eng->n_wide, wt_start));
   CU(up(eng->wide_tiles + 2 * eng->n_wide, wt_narrow));
+  CU(up(eng->wide_tiles + 3 * eng->n_wide, wt_len));
   CU(up(eng->batch_prob, bprob));
   CU(up(eng->batch_idx, bidx));
   CU(up(eng->term_ep, term_ep));
   CU(up(eng->ep_prob, ep_prob));
-  CU(cudaMemsetAsync(eng->err_flag, 0, sizeof(int), s));
   CU(cudaStreamSynchronize(s));   // staging vectors go out of scope
 
   if (eng->max_seg > 16384) return fail(TW_ERR_RANGE_LIMIT, "bind: a service has more than 16384 spans per list (sort limit)");
@@ -260,7 +285,9 @@ int tw_prepare(tw_engine* eng, void* stream_) {
   CU(cudaSetDevice(eng->device));
   CU(launch_prev_index(eng->dev, eng->prev_idx, s));
   CU(launch_sort_ends(eng->dev, eng->in_end_sorted, eng->out_end_sorted, eng->max_seg, eng->err_flag, s));
-  eng->launches += 2;
+  TileList tl{eng->score_tiles, eng->score_tiles + eng->n_tiles, eng->n_tiles, kS3Tile};
+  CU(launch_tile_meta(eng->dev, tl, eng->tile_win, s));
+  eng->launches += 3;
   return TW_OK;
 }
 
@@ -279,6 +306,23 @@ int tw_engine_status(tw_engine* eng, void* stream_) {
 }
 
 int64_t tw_engine_launch_count(const tw_engine* eng) { return eng ? eng->launches : 0; }
+
+int tw_engine_tile_stats(tw_engine* eng, int64_t* n_tiles, int64_t* n_redone, void* stream_) {
+  if (!eng || !eng->bound) return fail(TW_ERR_INVALID, "tw_engine_tile_stats: no batch bound");
+  cudaStream_t s = (cudaStream_t)stream_;
+  CU(cudaSetDevice(eng->device));
+  if (n_tiles) *n_tiles = eng->n_tiles;
+  if (n_redone) {
+    std::vector<uint8_t> h((size_t)eng->n_tiles);
+    *n_redone = 0;
+    if (eng->windows_valid) {
+      CU(cudaMemcpyAsync(h.data(), eng->tile_overflow, h.size(), cudaMemcpyDeviceToHost, s));
+      CU(cudaStreamSynchronize(s));
+      for (uint8_t f : h) *n_redone += f != 0;
+    }
+  }
+  return TW_OK;
+}
 
 static int need_bound(tw_engine* eng, const char* who) {
   if (!eng || !eng->bound) return fail(TW_ERR_INVALID, "%s: no batch bound", who);
@@ -304,21 +348,42 @@ int tw_score_topk(tw_engine* eng, const tw_params* params, const tw_score_out* o
     return fail(TW_ERR_INVALID, "tw_score_topk: params given but topk outputs missing");
   if ((out->used_lo != nullptr) != (out->used_bits != nullptr) || (out->used_lo != nullptr) != (out->used_wide != nullptr))
     return fail(TW_ERR_INVALID, "tw_score_topk: used_lo / used_bits / used_wide go together");
-  TileList narrow{eng->narrow_tiles, eng->narrow_tiles + eng->n_narrow, eng->n_narrow, kScoreTile};
-  TileList wide{eng->wide_tiles, eng->wide_tiles + eng->n_wide, eng->n_wide, kWideThreads - 1};
-  static const bool use_v1 = getenv("TW_SCORE_V1") != nullptr;   // A/B switch for profiling
-  if (params && !use_v1) {
-    // work-balanced scoring kernel for the narrow tiles; bitmap-overflow tiles are redone by the
-    // wide instantiation of k_score
-    CU(launch_score2(eng->dev, *params, *out, narrow, eng->prev_idx, eng->narrow_overflow, eng->err_flag,
-                     (cudaStream_t)stream));
-    CU(launch_score(eng->dev, params, *out, narrow, wide, eng->prev_idx, eng->narrow_overflow, eng->err_flag,
-                    (cudaStream_t)stream, true));
-  } else {
-    CU(launch_score(eng->dev, params, *out, narrow, wide, eng->prev_idx, eng->narrow_overflow, eng->err_flag,
-                    (cudaStream_t)stream));
+  const int keep = (out->flags & TW_SCORE_KEEP_WINDOWS) != 0;
+  if (keep && !eng->windows_valid)
+    return fail(TW_ERR_INVALID, "tw_score_topk: TW_SCORE_KEEP_WINDOWS before any full call on this batch");
+  if (keep && !params) return TW_OK;   // nothing to do
+  cudaStream_t s = (cudaStream_t)stream;
+  tw_score_out o = *out;
+  if (!o.used_lo) {                    // the perfect-cut pass reads the maps: keep them in engine scratch
+    const size_t nt = (size_t)eng->dev_n_tuple;
+    CU(eng->alloc(&eng->own_used_lo, nt));
+    CU(eng->alloc(&eng->own_used_bits, 2 * nt));
+    CU(eng->alloc(&eng->own_used_wide, (size_t)eng->dev.n_in_total));
+    o.used_lo = eng->own_used_lo;
+    o.used_bits = eng->own_used_bits;
+    o.used_wide = eng->own_used_wide;
   }
-  eng->launches += 2;
+  ScoreTiles st;
+  st.tile_prob = eng->score_tiles;
+  st.tile_start = eng->score_tiles + eng->n_tiles;
+  st.tile_win = eng->tile_win;
+  st.overflow = eng->tile_overflow;
+  st.n_tiles = eng->n_tiles;
+  for (int q = 0; q <= TW_MAX_E; ++q) st.class_off[q] = eng->class_off[q];
+  TileList wide{eng->wide_tiles, eng->wide_tiles + eng->n_wide, eng->n_wide, kWideThreads - 1,
+                eng->wide_tiles + 3 * eng->n_wide};
+  int nl = 0;
+  // work-balanced scoring kernel (one launch per E present); flagged tiles are redone by the
+  // sequential kernel; PerfectCut flags from the candidate maps
+  CU(launch_score3(eng->dev, params, o, keep, st, eng->prev_idx, eng->device, &nl, s));
+  CU(launch_score_redo(eng->dev, params, o, wide, eng->prev_idx, eng->tile_overflow, eng->device, eng->err_flag, s));
+  ++nl;
+  if (!keep) {
+    CU(launch_cut(eng->dev, o, st, eng->prev_idx, s));
+    ++nl;
+    eng->windows_valid = true;
+  }
+  eng->launches += nl;
   return TW_OK;
 }
 

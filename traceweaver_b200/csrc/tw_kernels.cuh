@@ -8,9 +8,8 @@
 namespace tw {
 
 // ---- score kernel geometry (tw_score.cu) ----------------------------------------------------
-constexpr int kScoreThreads = 128;               // one in-span per thread
-constexpr int kScoreTile = kScoreThreads - 1;    // in-spans per CTA; the last thread enumerates
-                                                 // the tile's carry-in "prev" in-span (PerfectCut)
+constexpr int kS3Threads = 128;                  // tw_score3.cu: one CTA = one tile, one warp = 32 in-spans
+constexpr int kS3Tile = 128;                     // in-spans per tile
 constexpr int kStageSpans = 1536;                // out spans staged in shared memory per tile
 constexpr int kTblCap = 3072;                    // term-table slots per CTA round (tw_core.cuh)
 constexpr int kWarpTblCap = 192;                 // term-table slots per stitch warp (search path only)
@@ -30,15 +29,31 @@ struct TileList {
   const int32_t* tile_start;
   int n_tiles;
   int tile_len;
+  const int32_t* tile_cnt = nullptr;   // optional explicit length per tile (<= tile_len)
+};
+
+// The scoring tiles of a bound batch, grouped by the number of eps of their problem (the scoring
+// kernel is templated on E): class E occupies tiles [class_off[E-1], class_off[E]).
+struct ScoreTiles {
+  const int32_t* tile_prob;
+  const int32_t* tile_start;
+  const int32_t* tile_win;     // [n_tiles][2*TW_MAX_E]: candidate slice (first index, length) per ep
+  uint8_t* overflow;           // [n_tiles] 1 = redone by the sequential kernel
+  int n_tiles;
+  int class_off[TW_MAX_E + 1];
 };
 
 cudaError_t launch_prev_index(const tw_batch& b, int32_t* prev_idx, cudaStream_t s);
-cudaError_t launch_score(const tw_batch& b, const tw_params* prm, const tw_score_out& out,
-                         const TileList& narrow, const TileList& wide, const int32_t* prev_idx,
-                         uint8_t* narrow_overflow, int* err_flag, cudaStream_t s, bool wide_only = false);
-cudaError_t launch_score2(const tw_batch& b, const tw_params& prm, const tw_score_out& out,
-                          const TileList& narrow, const int32_t* prev_idx, uint8_t* narrow_overflow,
-                          int* err_flag, cudaStream_t s);
+cudaError_t launch_tile_meta(const tw_batch& b, const TileList& tiles, int32_t* tile_win, cudaStream_t s);
+cudaError_t launch_score3(const tw_batch& b, const tw_params* prm, const tw_score_out& out, int keep_windows,
+                          const ScoreTiles& st, const int32_t* prev_idx, int device, int* n_launches,
+                          cudaStream_t s);
+cudaError_t launch_cut(const tw_batch& b, const tw_score_out& out, const ScoreTiles& st, const int32_t* prev_idx,
+                       cudaStream_t s);
+// sequential redo of the tiles the scoring kernel flagged (wide tiles subdivide scoring tiles)
+cudaError_t launch_score_redo(const tw_batch& b, const tw_params* prm, const tw_score_out& out,
+                              const TileList& wide, const int32_t* prev_idx, uint8_t* tile_overflow,
+                              int device, int* err_flag, cudaStream_t s);
 cudaError_t launch_stitch(const tw_batch& b, const tw_params& prm, const uint8_t* cut,
                           const tw_score_out& spec, const tw_pass_out& out, uint32_t* taken_words, size_t taken_n_words,
                           long long node_limit, int* err_flag, cudaStream_t s);

@@ -1,5 +1,7 @@
-// tw_score.cu — candidate enumeration + likelihood scoring + top-K on the undeleted lists, and
-// the perfect-cut flags, for every in-span of a batch.
+// tw_score.cu — the SEQUENTIAL form of the scoring pass (one in-span per thread, depth-first
+// enumeration, the reference's own tie order), used to redo the tiles the work-balanced kernel
+// (tw_score3.cu) flags, plus the prev-index scan.  Candidate enumeration + likelihood scoring +
+// top-K on the undeleted lists, and the perfect-cut flags.
 //
 // Replaces (reference: .../algorithms/traceweaver_v3.py = V3, traceweaver_v1.py = V1)
 //   FindTopKAssignments(K=5, out_span_partitions)   V3:1185  (DfsTraverseX V3:292-351,
@@ -110,7 +112,7 @@ __device__ __forceinline__ void score_tile(const tw_batch& b, const tw_params& p
   }
   const ProbView& v = sm.v;
   const int n = v.n_in;
-  cnt = min(tiles.tile_len, n - i0);
+  cnt = min(tiles.tile_cnt ? tiles.tile_cnt[t] : tiles.tile_len, n - i0);
   const int E = v.E;
   const bool helper = (tid == T - 1) && (i0 >= 1);
   const bool worker = tid < cnt;
@@ -166,7 +168,7 @@ __device__ __forceinline__ void score_tile(const tw_batch& b, const tw_params& p
   int batch0 = i0 / TW_PARAM_BATCH;
   if (has_params) {
     if (prm.mode == TW_PARAMS_GAUSS_BATCHED) {
-      // a tile of kScoreTile (=127) in-spans can touch three 100-span batches
+      // a tile can touch three 100-span batches
       int nrec = 3 * v.n_terms * TW_GAUSS_REC;
       int nb = (n + TW_PARAM_BATCH - 1) / TW_PARAM_BATCH;
       const double* src = prm.gauss + (prm.prob_gauss_off[p] + (int64_t)batch0 * v.n_terms) * TW_GAUSS_REC;
@@ -373,37 +375,25 @@ k_score(tw_batch b, tw_params prm, int has_params, tw_score_out out, TileList ti
   }
 }
 
-cudaError_t launch_score(const tw_batch& b, const tw_params* prm, const tw_score_out& out,
-                         const TileList& narrow, const TileList& wide, const int32_t* prev_idx,
-                         uint8_t* narrow_overflow, int* err_flag, cudaStream_t s, bool wide_only) {
+cudaError_t launch_score_redo(const tw_batch& b, const tw_params* prm, const tw_score_out& out,
+                              const TileList& wide, const int32_t* prev_idx, uint8_t* tile_overflow,
+                              int device, int* err_flag, cudaStream_t s) {
   tw_params dummy;
   dummy.mode = TW_PARAMS_MIXTURE; dummy.reserved0 = 0;
   dummy.prob_gauss_off = nullptr; dummy.gauss = nullptr; dummy.mix = nullptr;
   const tw_params& pr = prm ? *prm : dummy;
-  using SmN = ScoreSmem<kScoreThreads, kNarrowW>;
   using SmW = ScoreSmem<kWideThreads, kWideW>;
-  auto kn = k_score<kScoreThreads, kNarrowW>;
   auto kw = k_score<kWideThreads, kWideW>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e1 = cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmN));
+  static bool attr_done[64] = {false};   // per device: a process may drive several GPUs
+  if (device >= 0 && device < 64 && !attr_done[device]) {
     cudaError_t e2 = cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmW));
-    if (e1 != cudaSuccess) return e1;
     if (e2 != cudaSuccess) return e2;
-    attr_done = true;
+    attr_done[device] = true;
   }
-  cudaError_t e = cudaSuccess;
-  if (!wide_only) {   // otherwise k_score2 has run the narrow tiles and set the overflow flags
-    e = cudaMemsetAsync(narrow_overflow, 0, (size_t)narrow.n_tiles, s);
-    if (e != cudaSuccess) return e;
-    kn<<<narrow.n_tiles, kScoreThreads, sizeof(SmN), s>>>(b, pr, prm != nullptr, out, narrow, prev_idx,
-                                                          narrow_overflow, 0, err_flag);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-  }
+  if (wide.n_tiles == 0) return cudaSuccess;
   const int wide_grid = wide.n_tiles < 148 * 16 ? wide.n_tiles : 148 * 16;
   kw<<<wide_grid, kWideThreads, sizeof(SmW), s>>>(b, pr, prm != nullptr, out, wide, prev_idx,
-                                                  narrow_overflow, 1, err_flag);
+                                                  tile_overflow, 1, err_flag);
   return cudaGetLastError();
 }
 

@@ -100,6 +100,18 @@ class Engine:
     def launch_count(self):
         return int(self.lib.tw_engine_launch_count(self.h))
 
+    def _tile_stats(self):
+        nt, nr = C.c_int64(0), C.c_int64(0)
+        _lib.check(self.lib.tw_engine_tile_stats(self.h, C.byref(nt), C.byref(nr), self.stream), "tw_engine_tile_stats")
+        return int(nt.value), int(nr.value)
+
+    def tile_count(self):
+        return self._tile_stats()[0]
+
+    def redo_tile_count(self):
+        """Scoring tiles the last score() handed to the sequential kernel (syncs the stream)."""
+        return self._tile_stats()[1]
+
     # -- kernels ---------------------------------------------------------------------------------
     def params_pass0(self) -> Params:
         n_rec = int(self.hb.prob_gauss_off[-1])
@@ -115,8 +127,10 @@ class Engine:
         t = _to_device(np.asarray(gauss, np.float64).reshape(-1, _abi.TW_GAUSS_REC), self.device)
         return Params(_abi.TW_PARAMS_GAUSS_BATCHED, t, self.d["prob_gauss_off"])
 
-    def score(self, params: Params = None, out=None, want_used=False):
-        """tw_score_topk.  want_used: also emit the candidate maps tw_stitch's fast path needs."""
+    def score(self, params: Params = None, out=None, want_used=False, keep_windows=False):
+        """tw_score_topk.  want_used: also emit the candidate maps tw_stitch's fast path needs.
+        keep_windows: `out` already holds cut / used maps from an earlier call on this batch (they
+        depend on the span arrays only); only the top-K lists are produced."""
         dev = self.device
         n, nt = self.n_in, self.n_tuple
         if out is None:
@@ -132,6 +146,7 @@ class Engine:
             out.setdefault("topk_idx", torch.empty(_abi.TW_K * nt, dtype=torch.int32, device=dev))
             out.setdefault("topk_cnt", torch.empty(n, dtype=torch.uint8, device=dev))
         s = self._score_struct(out)
+        s.flags = _abi.TW_SCORE_KEEP_WINDOWS if keep_windows else 0
         ps = params.struct() if params is not None else None
         _lib.check(self.lib.tw_score_topk(self.h, C.byref(ps) if ps is not None else None, C.byref(s),
                                           self.stream), "tw_score_topk")

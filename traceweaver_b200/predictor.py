@@ -48,7 +48,8 @@ def solve_bound(eng: Engine, seed_select=10, truth_assign=None, term_order=None,
         base = eng.gmm_stream_draws(dt, ct)
     p1 = eng.gmm_refit(delays, counts, seed_select=seed_select, prob_base_skip=base, term_order=term_order)
     # top_k_2 of the last iteration -> all_topk_assignments; candidate maps are parameter independent
-    top = eng.score(p1, out=dict(used_lo=sc["used_lo"], used_bits=sc["used_bits"], used_wide=sc["used_wide"]))
+    top = eng.score(p1, out=dict(used_lo=sc["used_lo"], used_bits=sc["used_bits"], used_wide=sc["used_wide"],
+                                 cut=sc["cut"]), keep_windows=True)
     if after_score is not None:
         after_score(top)
     r1 = eng.stitch(p1, sc["cut"], undeleted=top)  # iteration 1
