@@ -40,6 +40,12 @@ extern "C" {
 #define TW_PARAM_BATCH 100     /* batch_size              traceweaver_v3.py:1107                */
 #define TW_PARAM_NBATCHES 10   /* nbatches                traceweaver_v3.py:599                 */
 #define TW_WEIGHT_OFFSET 10000.0 /* MWIS vertex weight    traceweaver_v3.py:1260                */
+/* Independent sets whose total weights differ by less than this are TIED.  The reference hands the
+ * instance to Gurobi (traceweaver_v3.py:1411), which returns an arbitrary optimum on ties; the engine
+ * and the oracle both return, per connected component of the window's conflict graph, the FIRST tied
+ * optimum in depth-first order (in-spans ascending; ranks ascending, "unassigned" last).  The
+ * tolerance makes that choice independent of the order in which a solver adds the weights up. */
+#define TW_MWIS_TIE_TOL 1e-6
 #define TW_GMM_MAX_COMP 5      /* max mixture components  traceweaver_v3.py:768                 */
 #define TW_GAUSS_REC 3         /* doubles per pass-0 record: mu, sigma, log(sigma)              */
 #define TW_MIX_REC 21          /* doubles per mixture record: k, pc[5], mu*pc[5], logdet[5], logw[5] */

@@ -387,7 +387,8 @@ int two_score_problem(const tw_batch* b, int p, const tw_params* prm, const tw_s
  * Vertices (ind, rank) with weight 10000+score; edges: same ind, or a shared out span at the
  * same tuple position (AssignmentIntersect V3:1276-1281).  Branch and bound over in-spans in
  * window order: pick one compatible candidate or none.  Vertices with weight <= 0 are never
- * chosen.
+ * chosen.  Ties (totals within TW_MWIS_TIE_TOL; Gurobi's choice is arbitrary
+ * there) go to the first leaf of this depth-first order.
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
   const prob_t* v; int nw;
@@ -408,10 +409,10 @@ static void mw_rec(mwis_t* m, int k, double cur_w) {
   if (m->nodes > TWO_MWIS_NODE_LIMIT) return;
   m->nodes++;
   if (k == m->nw) {
-    if (cur_w > m->best_w) { m->best_w = cur_w; memcpy(m->best, m->cur, sizeof(int) * (size_t)m->nw); }
+    if (cur_w > m->best_w + TW_MWIS_TIE_TOL) { m->best_w = cur_w; memcpy(m->best, m->cur, sizeof(int) * (size_t)m->nw); }
     return;
   }
-  if (cur_w + m->ub_suffix[k] <= m->best_w) return;
+  if (cur_w + m->ub_suffix[k] <= m->best_w + TW_MWIS_TIE_TOL) return;
   for (int r = 0; r < m->cand[k].n; ++r) {
     if (!(m->w[k][r] > 0.0)) continue;
     int ok = 1;

@@ -10,7 +10,7 @@ python bench.py --steps 5 --warmup 3 > gpurun_out/bench_${R}_builder.json 2> gpu
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_${R}_reference.json 2>> gpurun_out/bench_${R}_err.log
 ncu --metrics gpu__time_duration.sum --clock-control none -s 45 -c 75 --csv --log-file gpurun_out/launches_$R.csv \
     python scripts/profile_run.py 8192 > gpurun_out/ncu_launch_$R.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_score2 -s 3 -c 1 -o gpurun_out/prof_${R}_score2 -f \
+ncu --set full --clock-control none --import-source on -k regex:k_score3 -s 3 -c 1 -o gpurun_out/prof_${R}_score3 -f \
     python scripts/profile_run.py 2048 > gpurun_out/ncu_full_$R.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_stitch -s 2 -c 1 -o gpurun_out/prof_${R}_stitch -f \
     python scripts/profile_run.py 2048 >> gpurun_out/ncu_full_$R.log 2>&1

@@ -52,7 +52,7 @@ static long long enumerate_with_tables(const ProbView& v, const ParamView& pv, i
                              if (bit >= 32 * W) { *overflow = 1; continue; }
                              mark[e * W + (bit >> 5)] |= 1u << (bit & 31);
                            }
-                         topk_offer(v, part[lane], table_score(v, r, lo_abs, tbl.data(), c, ce), c);
+                         topk_offer_sorted(v, part[lane], table_score(v, r, lo_abs, tbl.data(), c, ce), c);
                        });
     }
     int head[32] = {0};
@@ -124,7 +124,7 @@ extern "C" int twe_score_problem(const tw_batch* b, int p, const tw_params* prm,
       lo[e] = lower_bound(w[e].s, w[e].n, v.is[i]);
       lo_abs[(size_t)i * TW_MAX_E + e] = lo[e];
     }
-    TopK tk; tk.n = 0;
+    TopK tk; tk.clear();
     long long leaves = 0;
     uint32_t* mine = &used[(size_t)i * TW_MAX_E * W];
     ParamView pv;
@@ -148,6 +148,7 @@ extern "C" int twe_score_problem(const tw_batch* b, int p, const tw_params* prm,
                   if (prm) topk_offer(v, tk, score_tuple(v, pv, in_s, in_e, cs, ce), c);
                 });
     }
+    topk_finish(v, tk);
     out->n_feasible[v.in_off + i] = (int32_t)leaves;
     if (prm && out->topk_score) {
       out->topk_cnt[v.in_off + i] = (uint8_t)tk.n;
@@ -204,7 +205,7 @@ extern "C" int twe_stitch_problem(const tw_batch* b, int p, const tw_params* prm
       int lo[TW_MAX_E];
       for (int e = 0; e < v.E; ++e) lo[e] = lower_bound_from(w[e].s, w[e].n, cursor[e], v.is[i]);
       if (l == 0) for (int e = 0; e < v.E; ++e) cursor[e] = lo[e];
-      TopK tk; tk.n = 0;
+      TopK tk; tk.clear();
       long long leaves = 0;
       ParamView pv = param_view(prm, v, p, i);
       int64_t in_s = v.is[i], in_e = v.ie[i];
@@ -222,6 +223,7 @@ extern "C" int twe_stitch_problem(const tw_batch* b, int p, const tw_params* prm
                     topk_offer(v, tk, score_tuple(v, pv, in_s, in_e, cs, ce), c);
                   });
       }
+      topk_finish(v, tk);
       out->n_cand[v.in_off + i] = (int32_t)leaves;
       wb->cnt[l] = tk.n;
       for (int k = 0; k < tk.n; ++k) {
@@ -302,7 +304,7 @@ extern "C" long long twe_mwis_window(int nw, int E, const int* cnt, const double
 // The warp-parallel solver of tw_stitch.cu (stitch_small_window) restated for one thread: candidate
 // (k, r) = "lane" 5k + r, conflict masks per candidate, components of the in-span conflict graph,
 // exhaustive mixed-radix enumeration (lowest in-span most significant, digit cnt = unassigned),
-// largest total first, then the lowest combination index.  Returns 0 when the kernel would fall back
+// the lowest combination index among the totals tied with the largest (TW_MWIS_TIE_TOL).  Returns 0 when the kernel would fall back
 // to the sequential solver (E == 1 component of >= 3 in-spans, or more than `space_cap` leaves).
 extern "C" int twe_small_window(int nw, int E, const int* cnt_in, const double* score, const int* idx,
                                 int* chosen, int space_cap) {
@@ -352,30 +354,36 @@ extern "C" int twe_small_window(int nw, int E, const int* cnt_in, const double* 
       if ((comp >> a) & 1u) space *= (a < nw ? cnt_in[a] : 0) + 1;
     }
     if (space > space_cap) return 0;
-    double best_w = -1.0;
-    int best_idx = 0x7fffffff;
-    for (int lane = 0; lane < 32; ++lane) {          // lanes stride over the leaves, then the warp reduces
-      double lw = -1.0;
-      int li = 0x7fffffff;
-      for (int id = lane; id < space; id += 32) {
-        int rem = id;
-        uint32_t sel = 0;
-        double tot = 0.0;
-        bool ok = true;
-        for (int a = 0; a < KW; ++a) {
-          if (!((comp >> a) & 1u)) continue;
-          int d = rem / stride[a];
-          rem -= d * stride[a];
-          if (d < cnt_in[a]) {
-            int c = TW_K * a + d;
-            if (!(cw[c] > 0.0) || (conf[c] & sel)) ok = false;
-            sel |= 1u << c;
-            tot = tot + cw[c];
-          }
+    // two passes like the kernel: the maximum total, then the lowest leaf index tied with it
+    auto leaf_total = [&](int id, bool& ok) {
+      int rem = id;
+      uint32_t sel = 0;
+      double tot = 0.0;
+      ok = true;
+      for (int a = 0; a < KW; ++a) {
+        if (!((comp >> a) & 1u)) continue;
+        int d = rem / stride[a];
+        rem -= d * stride[a];
+        if (d < cnt_in[a]) {
+          int c = TW_K * a + d;
+          if (!(cw[c] > 0.0) || (conf[c] & sel)) ok = false;
+          sel |= 1u << c;
+          tot = tot + cw[c];
         }
-        if (ok && tot > lw) { lw = tot; li = id; }
       }
-      if (lw > best_w || (lw == best_w && li < best_idx)) { best_w = lw; best_idx = li; }
+      return tot;
+    };
+    double best_w = -1.0;
+    for (int id = 0; id < space; ++id) {
+      bool ok;
+      const double tot = leaf_total(id, ok);
+      if (ok && tot > best_w) best_w = tot;
+    }
+    int best_idx = 0x7fffffff;
+    for (int id = 0; id < space && best_idx == 0x7fffffff; ++id) {
+      bool ok;
+      const double tot = leaf_total(id, ok);
+      if (ok && tot >= best_w - TW_MWIS_TIE_TOL) best_idx = id;
     }
     int rem = best_idx;
     for (int a = 0; a < KW; ++a) {

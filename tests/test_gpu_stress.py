@@ -30,14 +30,20 @@ CASES = {
     "tiny": ("hotel_search", 16, 2, 100.0),                  # two in-spans: the minimum the reference accepts
     "big_service": ("hotel_frontend", 2, 5000, 100.0),       # taken bitmap in global memory
     "very_wide": ("single", 2, 300, 60000.0),                # > 64 candidates per in-span: wide bitmaps (score only)
+    # millisecond clocks: equal starts, exact score ties (heapq order, tests/test_ties.py) and tied
+    # MWIS optima (TW_MWIS_TIE_TOL) are common
+    "par3_ms": ("ali_par3", 4, 300, 60.0, 1000),
+    "chain2_ms": ("ali_chain2", 4, 300, 100.0, 1000),
+    "nginx_2ms": ("media_nginx_cal", 3, 200, 60.0, 2000),
 }
 
 
 def _batch(name):
     from traceweaver_b200 import synth
     from traceweaver_b200.batch import build_batch_from_blocks
-    shape, S, n, load = CASES[name]
-    blocks = [synth.make_block(shape, S, n, load, seed=123)]
+    shape, S, n, load = CASES[name][:4]
+    quantum = CASES[name][4] if len(CASES[name]) > 4 else 1
+    blocks = [synth.make_block(shape, S, n, load, seed=123, quantum_us=quantum)]
     return blocks, build_batch_from_blocks(blocks)
 
 
@@ -110,7 +116,7 @@ def test_each_pass_matches_oracle(engine, name):
     assert np.array_equal(_np(st1["mis_rank"]), o_st1["mis_rank"])
 
 
-@pytest.mark.parametrize("name", ["nginx_parallel", "single_ep", "tiny"])
+@pytest.mark.parametrize("name", ["nginx_parallel", "single_ep", "tiny", "par3_ms", "nginx_2ms"])
 def test_whole_path_matches_oracle(name):
     from oracle import tw_oracle
     from traceweaver_b200.api import BatchSolver

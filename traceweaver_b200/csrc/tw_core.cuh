@@ -253,12 +253,21 @@ TW_HD double score_tuple(const ProbView& v, const ParamView& pv, int64_t in_s, i
 // score, then the first tuple position whose span differs decides by start (spans.py:51).
 // ---------------------------------------------------------------------------------------------
 struct TopK {
-  double score[TW_K];
-  int idx[TW_K][TW_MAX_E];
+  double score[TW_K + 1];
+  int idx[TW_K + 1][TW_MAX_E];
+  uint8_t heap[TW_K + 1];   // heap[0..n) = slots in CPython heapq array order; heap[n] = a free slot
   int n;
+  TW_HD void clear() {
+    n = 0;
+    for (int k = 0; k <= TW_K; ++k) heap[k] = (uint8_t)k;
+  }
 };
 
-// a < b in the reference's (score, stack) order
+// a < b in the reference's (score, stack) order: tuple comparison takes the score first; on equal
+// scores the stacks are compared element by element, the first position holding two different Span
+// objects decides by Span.__lt__ = start_mus (spans.py:51).  Two different spans with the same start
+// are neither smaller: a < b and b < a are both false, and then the ORDER OF THE OPERATIONS decides
+// where the entries end up — which is why topk_offer below replays heapq itself.
 TW_HD bool cand_less(const ProbView& v, double sa, const int* ca, double sb, const int* cb) {
   if (sa < sb) return true;
   if (!(sa == sb)) return false;
@@ -267,7 +276,84 @@ TW_HD bool cand_less(const ProbView& v, double sa, const int* ca, double sb, con
   return false;
 }
 
+TW_HD bool topk_slot_less(const ProbView& v, const TopK& tk, int a, int b) {
+  return cand_less(v, tk.score[a], tk.idx[a], tk.score[b], tk.idx[b]);
+}
+
+// heapq._siftdown: the entry at `pos` moves towards the root while it is smaller than its parent
+TW_HD void topk_toward_root(const ProbView& v, TopK& tk, int startpos, int pos) {
+  const uint8_t item = tk.heap[pos];
+  while (pos > startpos) {
+    const int parent = (pos - 1) >> 1;
+    if (!topk_slot_less(v, tk, item, tk.heap[parent])) break;
+    tk.heap[pos] = tk.heap[parent];
+    pos = parent;
+  }
+  tk.heap[pos] = item;
+}
+
+// heapq._siftup: the smaller child is pulled up all the way to a leaf (the right child on
+// "not left < right"), the displaced entry is placed there and moved back towards the root
+TW_HD void topk_toward_leaf(const ProbView& v, TopK& tk, int pos) {
+  const int startpos = pos, endpos = tk.n;
+  const uint8_t item = tk.heap[pos];
+  int child = 2 * pos + 1;
+  while (child < endpos) {
+    const int right = child + 1;
+    if (right < endpos && !topk_slot_less(v, tk, tk.heap[child], tk.heap[right])) child = right;
+    tk.heap[pos] = tk.heap[child];
+    pos = child;
+    child = 2 * pos + 1;
+  }
+  tk.heap[pos] = item;
+  topk_toward_root(v, tk, startpos, pos);
+}
+
+// V3:305-307: heapq.heappush(top_assignments, (score, stack)); if len > K: heapq.heappop(...).
+// Replayed literally (min-heap of at most K + 1 entries in heapq's array layout), so that the
+// surviving entries AND their array order are the reference's also when entries compare equal.
 TW_HD void topk_offer(const ProbView& v, TopK& tk, double score, const int* c) {
+  const int slot = tk.heap[tk.n];
+  tk.score[slot] = score;
+  for (int e = 0; e < v.E; ++e) tk.idx[slot][e] = c[e];
+  tk.n += 1;
+  topk_toward_root(v, tk, 0, tk.n - 1);
+  if (tk.n > TW_K) {                     // heappop: the last entry replaces the root
+    const uint8_t last = tk.heap[tk.n - 1], root = tk.heap[0];
+    tk.n -= 1;
+    tk.heap[tk.n] = root;                // the popped entry's slot is the free one
+    if (tk.n > 0) {
+      tk.heap[0] = last;
+      topk_toward_leaf(v, tk, 0);
+    }
+  }
+}
+
+// V3:461 `top_assignments.sort(reverse=True)`: a stable descending sort of the heap ARRAY (entries
+// that compare equal keep their array order).  Leaves rank k in score[k] / idx[k].
+TW_HD void topk_finish(const ProbView& v, TopK& tk) {
+  uint8_t ord[TW_K + 1];
+  for (int a = 0; a < tk.n; ++a) {
+    const uint8_t x = tk.heap[a];
+    int j = a - 1;
+    while (j >= 0 && topk_slot_less(v, tk, ord[j], x)) { ord[j + 1] = ord[j]; --j; }
+    ord[j + 1] = x;
+  }
+  double sc[TW_K];
+  int ix[TW_K][TW_MAX_E];
+  for (int k = 0; k < tk.n; ++k) {
+    sc[k] = tk.score[ord[k]];
+    for (int e = 0; e < v.E; ++e) ix[k][e] = tk.idx[ord[k]][e];
+  }
+  for (int k = 0; k < tk.n; ++k) {
+    tk.score[k] = sc[k];
+    for (int e = 0; e < v.E; ++e) tk.idx[k][e] = ix[k][e];
+  }
+}
+
+// Sorted-list variant (insert keeping the list descending; an entry that compares equal to a listed
+// one goes behind it).  Only exact where no two tuples compare equal; used to merge partial lists.
+TW_HD void topk_offer_sorted(const ProbView& v, TopK& tk, double score, const int* c) {
   int pos = tk.n;
   while (pos > 0 && cand_less(v, tk.score[pos - 1], tk.idx[pos - 1], score, c)) --pos;
   if (pos >= TW_K) return;
@@ -798,7 +884,7 @@ TW_HD_NOINLINE inline long long mwis_solve(WindowBuf& wb, int E, int nw, long lo
     while (level >= 0) {
       if (level == m) {
         ++nodes;
-        if (cur[m] > best_w) {
+        if (cur[m] > best_w + TW_MWIS_TIE_TOL) {   // a tied total never replaces an earlier leaf
           best_w = cur[m];
           for (int l = 0; l < m; ++l) best[l] = choice[l];
         }
@@ -809,7 +895,7 @@ TW_HD_NOINLINE inline long long mwis_solve(WindowBuf& wb, int E, int nw, long lo
       if (iter[level] == 0) {
         ++nodes;
         if (node_limit > 0 && nodes > node_limit) return -1;
-        if (cur[level] + ub[level] <= best_w) { --level; continue; }
+        if (cur[level] + ub[level] <= best_w + TW_MWIS_TIE_TOL) { --level; continue; }
       }
       int r = iter[level]++;
       if (r > wb.cnt[k]) { --level; continue; }

@@ -233,7 +233,7 @@ __device__ __forceinline__ void score_tile(const tw_batch& b, const tw_params& p
                 mark(c, ovf);
               });
     if (ovf) sm.overflow = 1;
-    if (worker) { TopK none; none.n = 0; write_out(none, leaves); }
+    if (worker) { TopK none; none.clear(); write_out(none, leaves); }
   }
   // ---- scoring: term tables in shared memory, evaluated by the whole CTA (see tw_core.cuh)
   if (has_params) {
@@ -269,7 +269,7 @@ __device__ __forceinline__ void score_tile(const tw_batch& b, const tw_params& p
         pv.mix = sm.prm;
         pv.etab = sm.etab;
         TopK tk;
-        tk.n = 0;
+        tk.clear();
         int leaves = 0;
         bool ovf = false;
         enumerate(v, in_s, in_e, w, lo, [](int, int) { return false; },
@@ -279,6 +279,7 @@ __device__ __forceinline__ void score_tile(const tw_batch& b, const tw_params& p
                     topk_offer(v, tk, score_tuple(v, pv, in_s, in_e, cs, ce), c);
                   });
         if (ovf) sm.overflow = 1;
+        topk_finish(v, tk);
         write_out(tk, leaves);
         pending = false;
       }
@@ -301,7 +302,7 @@ __device__ __forceinline__ void score_tile(const tw_batch& b, const tw_params& p
         const double* tbl = sm.tbl + offset;
         const uint8_t* sid = sm.sid + offset;
         TopK tk;
-        tk.n = 0;
+        tk.clear();
         int leaves = 0;
         bool ovf = false;
         enumerate(v, in_s, in_e, w, lo,
@@ -312,6 +313,7 @@ __device__ __forceinline__ void score_tile(const tw_batch& b, const tw_params& p
                     topk_offer(v, tk, table_score(v, r, lo_abs, tbl, c, ce), c);
                   });
         if (ovf) sm.overflow = 1;
+        topk_finish(v, tk);
         write_out(tk, leaves);
         pending = false;
       }
@@ -368,10 +370,19 @@ k_score(tw_batch b, tw_params prm, int has_params, tw_score_out out, TileList ti
     score_tile<T, W>(b, prm, has_params, out, tiles, blockIdx.x, prev_idx, overflow_flag, 0, err_flag, sm);
     return;
   }
-  for (int t = blockIdx.x; t < tiles.n_tiles; t += gridDim.x) {
-    if (!overflow_flag[tiles.tile_start[tiles.n_tiles + t]]) continue;   // uniform across the CTA
-    score_tile<T, W>(b, prm, has_params, out, tiles, t, prev_idx, overflow_flag, 1, err_flag, sm);
-    __syncthreads();                                                      // shared memory is re-used
+  // the flags of T wide tiles are read at once (one coalesced load + one ballot per 32); flagged
+  // tiles are rare, so a CTA mostly skims
+  static_assert(T == 32, "the redo scan is written for one warp per CTA");
+  for (int base = blockIdx.x * 32; base < tiles.n_tiles; base += gridDim.x * 32) {
+    const int t0 = base + (int)threadIdx.x;
+    const bool f = t0 < tiles.n_tiles && overflow_flag[tiles.tile_start[tiles.n_tiles + t0]] != 0;
+    unsigned m = __ballot_sync(0xffffffffu, f);
+    while (m) {
+      const int t = base + __ffs(m) - 1;
+      m &= m - 1u;
+      score_tile<T, W>(b, prm, has_params, out, tiles, t, prev_idx, overflow_flag, 1, err_flag, sm);
+      __syncthreads();                                                    // shared memory is re-used
+    }
   }
 }
 
@@ -391,7 +402,8 @@ cudaError_t launch_score_redo(const tw_batch& b, const tw_params* prm, const tw_
     attr_done[device] = true;
   }
   if (wide.n_tiles == 0) return cudaSuccess;
-  const int wide_grid = wide.n_tiles < 148 * 16 ? wide.n_tiles : 148 * 16;
+  const int chunks = (wide.n_tiles + 31) / 32;
+  const int wide_grid = chunks < 148 * 16 ? chunks : 148 * 16;
   kw<<<wide_grid, kWideThreads, sizeof(SmW), s>>>(b, pr, prm != nullptr, out, wide, prev_idx,
                                                   tile_overflow, 1, err_flag);
   return cudaGetLastError();

@@ -116,7 +116,6 @@ __device__ __forceinline__ bool stitch_small_window(StitchWarpSmem& sm, int E, i
     }
     if (space > kSmallSpace) return false;
     double best_w = -1.0;
-    int best_idx = 0x7fffffff;
     for (int idx = lane; idx < space; idx += 32) {
       int rem = idx;
       uint32_t sel = 0u;
@@ -136,13 +135,41 @@ __device__ __forceinline__ bool stitch_small_window(StitchWarpSmem& sm, int E, i
           }
         }
       }
-      if (ok && tot > best_w) { best_w = tot; best_idx = idx; }
+      if (ok && tot > best_w) best_w = tot;
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
       const double ow = __shfl_xor_sync(kAll, best_w, d);
+      best_w = ow > best_w ? ow : best_w;
+    }
+    // the first leaf (lowest index) whose total is tied with the maximum (TW_MWIS_TIE_TOL): what the
+    // sequential search returns, whatever the order in which the totals were rounded
+    int best_idx = 0x7fffffff;
+    for (int idx = lane; idx < space && best_idx == 0x7fffffff; idx += 32) {
+      int rem = idx;
+      uint32_t sel = 0u;
+      double tot = 0.0;
+      bool ok = true;
+#pragma unroll
+      for (int a = 0; a < kSmallWindow; ++a) {
+        if ((comp >> a) & 1u) {
+          const int d = rem / stride[a];
+          rem -= d * stride[a];
+          if (d < cnt[a]) {
+            const int c = TW_K * a + d;
+            const double wgt = sm.cw[c];
+            if (!(wgt > 0.0) || (sm.cconf[c] & sel)) ok = false;
+            sel |= 1u << c;
+            tot = tot + wgt;
+          }
+        }
+      }
+      if (ok && tot >= best_w - TW_MWIS_TIE_TOL) best_idx = idx;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
       const int oi = __shfl_xor_sync(kAll, best_idx, d);
-      if (ow > best_w || (ow == best_w && oi < best_idx)) { best_w = ow; best_idx = oi; }
+      best_idx = oi < best_idx ? oi : best_idx;
     }
     {
       int rem = best_idx;
@@ -440,13 +467,14 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
         pv.mix = mix_base;
         pv.etab = etab;
         TopK tk;
-        tk.n = 0;
+        tk.clear();
         int leaves = 0;
         enumerate(v, in_s, in_e, w, lo, is_taken,
                   [&](const int* c, const int64_t* cs, const int64_t* ce) {
                     if (leaves < 0x7fffffff) ++leaves;
                     topk_offer(v, tk, score_tuple(v, pv, in_s, in_e, cs, ce), c);
                   });
+        topk_finish(v, tk);
         publish(tk, leaves);
         pending = false;
       }
@@ -467,7 +495,7 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
         const double* tbl = sm.tbl + offset;
         const uint8_t* sid = sm.sid + offset;
         TopK tk;
-        tk.n = 0;
+        tk.clear();
         int leaves = 0;
         enumerate(v, in_s, in_e, w, lo,
                   [&](int e, int o) { return sid[o_last[e] + (o - lo_abs[e])] == TW_SLOT_INVALID; },
@@ -475,6 +503,7 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
                     if (leaves < 0x7fffffff) ++leaves;
                     topk_offer(v, tk, table_score(v, r, lo_abs, tbl, c, ce), c);
                   });
+        topk_finish(v, tk);
         publish(tk, leaves);
         pending = false;
       }

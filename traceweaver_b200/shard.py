@@ -71,7 +71,7 @@ def stream_spec(workload: str, n_services: int, n_in: int, seed: int, block_serv
         for cf in (1, 200, 1000, 4000, 10000, 15000):
             for s in ("ali_leaf", "ali_chain2", "ali_par3", "ali_chain4", "ali_leaf", "ali_chain2"):
                 replicas = 2 ** int(rng.integers(0, 13))
-                cycle.append((s, min(float(max(1, int(np.ceil(cf / replicas)))), 100.0), 1000))
+                cycle.append((s, min(float(max(1, int(np.ceil(cf / replicas)))), synth_max_load()), 1000))
     else:
         raise ValueError(workload)
     per = max(1, min(block_services, n_services // len(cycle)))
@@ -83,6 +83,12 @@ def stream_spec(workload: str, n_services: int, n_in: int, seed: int, block_serv
         left -= s
         k += 1
     return specs
+
+
+def synth_max_load() -> float:
+    """Load cap of the alibaba-shaped generator (synth.alibaba_stream explains the cap)."""
+    from . import synth
+    return synth.ALIBABA_MAX_LOAD
 
 
 def spec_span_counts(specs: Sequence[BlockSpec]) -> np.ndarray:
