@@ -184,7 +184,7 @@ def sample_blocks(blocks, per):
     return out
 
 
-def cpu_baseline(blocks, gpu_assign, n_services_sample, seed):
+def cpu_baseline(blocks, gpu_assign, n_services_sample, seed, gpu_assign_pass0=None):
     """oracle/ on the first services of every block (same inputs) + parity of the engine on them."""
     from traceweaver_b200.batch import build_batch_from_blocks
     per = max(1, n_services_sample // len(blocks))
@@ -192,18 +192,30 @@ def cpu_baseline(blocks, gpu_assign, n_services_sample, seed):
     shb = build_batch_from_blocks(sample)
     n_spans = int(sum(s.in_start.size * (1 + len(s.out_start)) for s in sample))
     res, dt, cores = run_oracle_pinned(shb, seed)
-    same, pos, cum = True, 0, 0
+    # iteration 0 alone (everything before the refit), untimed: the refit's BIC arg-min is ill-conditioned
+    # on samples with a handful of distinct delays (millisecond clocks; tests/gmm_conditioning.py), so the
+    # final comparison can differ there for reasons of summation order while iteration 0 must not
+    pass0 = None
+    if gpu_assign_pass0 is not None:
+        from oracle import tw_oracle
+        ob = tw_oracle.OracleBatch(shb)
+        g0 = ob.params_pass0()
+        pass0 = ob.stitch(ob.score(gauss=g0)["cut"], gauss=g0, want_topk=False)["assign"]
+    same, same0, pos, cum = True, True, 0, 0
     for b, s in zip(blocks, sample):
         S, n = b.in_start.shape
         E = len(b.out_start)
         k = s.in_start.shape[0]
         same = same and bool(np.array_equal(gpu_assign[cum:cum + k * n * E], res["assign"][pos:pos + k * n * E]))
+        if pass0 is not None:
+            same0 = same0 and bool(np.array_equal(gpu_assign_pass0[cum:cum + k * n * E], pass0[pos:pos + k * n * E]))
         cum += S * n * E
         pos += k * n * E
     return {"value": n_spans / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"first {per} services of each of the {len(blocks)} blocks ({shb.n_problems} services, "
                       f"{n_spans} spans), {dt:.1f} s wall, one pinned thread per physical core",
-            "engine_equals_oracle_on_sample": same}
+            "engine_equals_oracle_on_sample": same,
+            "engine_equals_oracle_iteration0_on_sample": same0 if pass0 is not None else None}
 
 
 def measure(args, blocks, hb, dev_index, steps, warmup, gather=None, rank=0, world=1, want_cpu=True,
@@ -263,6 +275,7 @@ def measure(args, blocks, hb, dev_index, steps, warmup, gather=None, rank=0, wor
     if gather is not None:
         mine = gather.shards(res["gathered"])[rank]
         gather_ok = bool(torch.equal(mine, res["assign"]))
+    assign_pass0 = res["assign_pass0"].cpu().numpy() if (want_cpu and rank == 0 and world == 1) else None
 
     # ---- roofline of the scoring kernel (GMM pass: the final top-K lists), CUDA events on our stream
     p1 = res["params_pass1"]
@@ -329,7 +342,7 @@ def measure(args, blocks, hb, dev_index, steps, warmup, gather=None, rank=0, wor
 
     cpu = None
     if want_cpu and rank == 0 and world == 1:
-        cpu = cpu_baseline(blocks, gpu_assign, cpu_sample or args.cpu_sample, args.seed)
+        cpu = cpu_baseline(blocks, gpu_assign, cpu_sample or args.cpu_sample, args.seed, assign_pass0)
     return dict(n_spans=n_spans, resident_ms=resident_ms, launches=launches, accuracy=acc, unassigned=unassigned,
                 roofline=roofline, e2e=e2e, cpu=cpu, gather_ok=gather_ok,
                 clocks=sampler.summary() if sampler else None)
@@ -443,7 +456,9 @@ def run_ours(args):
                               "e2e_value": r["n_spans"] * 3 / (r["e2e"]["ms"] * 1e-3),
                               "accuracy": r["accuracy"], "unassigned": r["unassigned"], "roofline": r["roofline"],
                               "cpu_baseline": r["cpu"],
-                              "engine_equals_oracle_on_sample": r["cpu"]["engine_equals_oracle_on_sample"]})
+                              "engine_equals_oracle_on_sample": r["cpu"]["engine_equals_oracle_on_sample"],
+                              "engine_equals_oracle_iteration0_on_sample":
+                                  r["cpu"]["engine_equals_oracle_iteration0_on_sample"]})
             except Exception as ex:       # an extra leg must not take the headline line down with it
                 extra.append({"workload": WORKLOAD_TEXT[wl], "error": repr(ex)[:300]})
         try:

@@ -105,7 +105,27 @@ try:
     print(" whole path")
     cmp("assign", res["assign"], ref["assign"], tup_off)
     cmp("mis_rank", res["mis_rank"], ref["mis_rank"], in_off)
-    cmp("topk_idx", res["topk_idx"], ref["topk_idx"], tup_off * 5)
+    nb = cmp("topk_idx", res["topk_idx"], ref["topk_idx"], tup_off * 5)
+    if nb:
+        a = res["topk_idx"].cpu().numpy(); b = ref["topk_idx"]
+        sa = res["topk_score"].cpu().numpy(); sb = ref["topk_score"]
+        flat = np.flatnonzero(a != b)
+        shown = 0
+        seen = set()
+        for f in flat:
+            pr = int(np.searchsorted(tup_off * 5, f, side="right") - 1)
+            E = int(hb.prob_ep_off[pr + 1] - hb.prob_ep_off[pr])
+            i = (int(f) - int(tup_off[pr]) * 5) // (5 * E)
+            if (pr, i) in seen:
+                continue
+            seen.add((pr, i))
+            gi = int(in_off[pr]) + i
+            o = 5 * (int(tup_off[pr]) + i * E)
+            print(f"   problem {pr} ({sample_name(pr)}) in-span {i}: engine idx {a[o:o+5*E].reshape(5, E).tolist()} scores {sa[gi].tolist()}")
+            print(f"   {' ' * 40} oracle idx {b[o:o+5*E].reshape(5, E).tolist()} scores {sb[gi].tolist()}")
+            shown += 1
+            if shown >= 4:
+                break
     cmp("n_cand", res["n_cand"], ref["n_cand_total"], in_off)
     cmp("mix 1e-6", res["params_pass1"].table, ref["mix"], tol=1e-6)
 except Exception as ex:

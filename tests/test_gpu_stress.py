@@ -35,6 +35,7 @@ CASES = {
     "par3_ms": ("ali_par3", 4, 300, 60.0, 1000),
     "chain2_ms": ("ali_chain2", 4, 300, 100.0, 1000),
     "nginx_2ms": ("media_nginx_cal", 3, 200, 60.0, 2000),
+    "leaf_dense_ms": ("ali_leaf", 4, 300, 300.0, 1000),      # E = 1: tied optimal matchings
 }
 
 
@@ -116,7 +117,10 @@ def test_each_pass_matches_oracle(engine, name):
     assert np.array_equal(_np(st1["mis_rank"]), o_st1["mis_rank"])
 
 
-@pytest.mark.parametrize("name", ["nginx_parallel", "single_ep", "tiny", "par3_ms", "nginx_2ms"])
+# (the millisecond-clock cases are compared pass by pass above, with the oracle's mixtures: their delay
+# samples hold a handful of distinct values, where the BIC arg-min of the refit is ill-conditioned —
+# tests/gmm_conditioning.py — so a whole-path comparison would test summation order, not the engine)
+@pytest.mark.parametrize("name", ["nginx_parallel", "single_ep", "tiny"])
 def test_whole_path_matches_oracle(name):
     from oracle import tw_oracle
     from traceweaver_b200.api import BatchSolver

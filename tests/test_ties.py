@@ -16,6 +16,7 @@ CASES = {
     "par3_ms": ("ali_par3", 3, 160, 100.0, 1000),
     "chain2_ms": ("ali_chain2", 3, 200, 100.0, 1000),
     "leaf_ms": ("ali_leaf", 3, 200, 100.0, 1000),
+    "leaf_dense_ms": ("ali_leaf", 4, 300, 300.0, 1000),      # E = 1: tied optimal matchings (Hungarian path)
     "nginx_2ms": ("media_nginx_cal", 2, 120, 60.0, 2000),
 }
 

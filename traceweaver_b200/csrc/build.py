@@ -45,5 +45,20 @@ def build(force=False, verbose=False):
     return OUT
 
 
+def build_profiling():
+    """libtw_b200_prof.so: the same sources with -DTW_PROFILE_PHASES (clock64 phase timers inside the
+    scoring / stitch / refit kernels; scripts/*_phase_profile.py read them).  Never used by the product."""
+    out = os.path.join(PKG, "libtw_b200_prof.so")
+    cmd = [NVCC] + FLAGS + ["-DTW_PROFILE_PHASES", "-o", out] + sources()
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        print(res.stdout)
+        raise RuntimeError("nvcc failed (profiling build)")
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--prof" in sys.argv:
+        print(build_profiling())
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

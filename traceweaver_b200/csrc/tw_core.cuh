@@ -159,7 +159,7 @@ static __constant__ double c_exp2_64[64] = {
     1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
 
 __device__ __forceinline__ void load_exp_table(double* tab) {   // block-wide; call before any early return
-  if (threadIdx.x < 64) tab[threadIdx.x] = c_exp2_64[threadIdx.x];
+  for (int x = threadIdx.x; x < 64; x += blockDim.x) tab[x] = c_exp2_64[x];
   __syncthreads();
 }
 
@@ -202,6 +202,33 @@ __device__ __forceinline__ double mix_logpdf_tab(const double* rec, double dt, c
     const double d = a[c] - amax;
     const double e = exp_neg(tab, d);
     s += d >= -40.0 ? e : 0.0;      // exp(d) < 2^-57 cannot change a sum that holds the maximum's 1.0
+  }
+  return dadd(log(s), amax);
+}
+// mix_logpdf_tab for callers whose whole warp evaluates the SAME record (k is warp-uniform): only the
+// k live components are computed.  Component for component the same operations in the same order as
+// mix_logpdf_tab (whose masked components add an exact 0.0), so the value is bit-identical.
+__device__ __forceinline__ double mix_logpdf_tab_uniform(const double* rec, double dt, const double* __restrict__ tab) {
+  const int k = (int)rec[0];
+  if (k == 0) return gauss_logpdf(rec + 1, dt);
+  double a[TW_GMM_MAX_COMP];
+  double amax = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < TW_GMM_MAX_COMP; ++c) {
+    if (c < k) {
+      const double y = dsub(dmul(dt, rec[1 + c]), rec[6 + c]);
+      a[c] = dadd(dadd(dmul(-0.5, dadd(TW_LOG_2PI, dmul(y, y))), rec[11 + c]), rec[16 + c]);
+      amax = a[c] > amax ? a[c] : amax;
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int c = 0; c < TW_GMM_MAX_COMP; ++c) {
+    if (c < k) {
+      const double d = a[c] - amax;
+      const double e = exp_neg(tab, d);
+      s += d >= -40.0 ? e : 0.0;
+    }
   }
   return dadd(log(s), amax);
 }
@@ -817,12 +844,87 @@ TW_HD_NOINLINE inline void assignment_solve(const WindowBuf& wb, const int* memb
       j0 = j1;
     } while (j0);
   }
+  // ---- tied optima (TW_MWIS_TIE_TOL): the canonical answer is the FIRST optimal solution in the
+  // depth-first order of the branch and bound (in-spans ascending; ranks ascending, "unassigned"
+  // last).  Every optimal matching lives in the equality subgraph of the final potentials (edges
+  // with zero reduced cost), so: fix the rows in order; a row takes its first tight option for which
+  // the remaining rows can still be matched along tight edges (one alternating-path search).  With no
+  // ties the only tight option is the matched one and this pass is O(m).
+  short rowcol[TW_WINDOW_CAP];
+  for (int l = 0; l < m; ++l) rowcol[l] = 0;
+  for (int j = 1; j <= M; ++j)
+    if (p[j] != 0) rowcol[p[j] - 1] = (short)j;
+  bool fixedc[TW_ASSIGN_MAX_COLS];
+  for (int j = 0; j <= M; ++j) fixedc[j] = false;
+  auto opt_col = [&](int l, int r) { return r < TW_K ? (int)ecol[l][r] : ncol + 1 + l; };
+  auto tight = [&](int l, int r) {
+    const int j = opt_col(l, r);
+    if (j < 0) return false;
+    const double c = r < TW_K ? -(TW_WEIGHT_OFFSET + wb.score[member[l]][r]) : 0.0;
+    return c - u[l + 1] - vv[j] <= TW_MWIS_TIE_TOL;
+  };
   for (int l = 0; l < m; ++l) best[l] = -1;
-  for (int j = 1; j <= ncol; ++j) {
-    if (p[j] == 0) continue;
-    const int l = p[j] - 1;
-    for (int r = TW_K - 1; r >= 0; --r)
-      if (ecol[l][r] == j) best[l] = r;   // (lists are sorted: the lowest rank is the heaviest edge)
+  for (int l = 0; l < m; ++l) {
+    for (int r = 0; r <= TW_K; ++r) {
+      if (!tight(l, r)) continue;
+      const int j = opt_col(l, r);
+      if (fixedc[j]) continue;
+      bool ok = rowcol[l] == j;
+      if (!ok) {
+        const int owner = p[j] - 1;               // row holding column j now (-1: free); never a fixed row
+        const int freed = rowcol[l];
+        if (owner < 0) {
+          p[freed] = 0; p[j] = (short)(l + 1); rowcol[l] = (short)j;
+          ok = true;
+        } else {
+          // re-match `owner` along tight edges: columns j and the fixed ones are closed, `freed` is free
+          short st_row[TW_WINDOW_CAP + 1], st_opt[TW_WINDOW_CAP + 1], st_col[TW_WINDOW_CAP + 1];
+          for (int q = 0; q <= M; ++q) used[q] = fixedc[q];
+          used[j] = true;
+          p[freed] = 0;
+          int depth = 0;
+          st_row[0] = (short)owner; st_opt[0] = 0;
+          bool found = false;
+          while (depth >= 0 && !found) {
+            const int x = st_row[depth];
+            bool pushed = false;
+            while (st_opt[depth] <= TW_K) {
+              const int rr = st_opt[depth]++;
+              if (!tight(x, rr)) continue;
+              const int jj = opt_col(x, rr);
+              if (used[jj]) continue;
+              used[jj] = true;
+              st_col[depth] = (short)jj;
+              if (p[jj] == 0) { found = true; break; }
+              st_row[depth + 1] = (short)(p[jj] - 1);
+              st_opt[depth + 1] = 0;
+              ++depth;
+              pushed = true;
+              break;
+            }
+            if (found) break;
+            if (!pushed) --depth;
+          }
+          if (found) {
+            for (int d = depth; d >= 0; --d) {     // shift every row on the path to its new column
+              const int x = st_row[d], jj = st_col[d];
+              p[jj] = (short)(x + 1);
+              rowcol[x] = (short)jj;
+            }
+            p[j] = (short)(l + 1);
+            rowcol[l] = (short)j;
+            ok = true;
+          } else {
+            p[freed] = (short)(l + 1);             // nothing was changed: restore
+          }
+        }
+      }
+      if (ok) {
+        fixedc[j] = true;
+        best[l] = r < TW_K ? r : -1;
+        break;
+      }
+    }
   }
 }
 

@@ -97,7 +97,7 @@ __device__ __forceinline__ void score_tile(const tw_batch& b, const tw_params& p
                                            int* __restrict__ err_flag, ScoreSmem<T, W>& sm) {
   const int tid = threadIdx.x;
   int i0, cnt, p;
-  if (tid < 64) sm.etab[tid] = c_exp2_64[tid];   // visible after the barrier below (load_view)
+  for (int x = tid; x < 64; x += T) sm.etab[x] = c_exp2_64[x];   // (T may be 32) visible after the barrier below
   p = tiles.tile_prob[t];
   i0 = tiles.tile_start[t];
 

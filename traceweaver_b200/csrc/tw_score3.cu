@@ -39,6 +39,32 @@
 
 namespace tw {
 
+// optional phase timers / work counters (build with -DTW_PROFILE_PHASES; scripts/score_phase_profile.py)
+#ifdef TW_PROFILE_PHASES
+__device__ unsigned long long g_score_phase[24];
+#define TW_CPHASE(k)                                                                 \
+  do {                                                                               \
+    if (lane == 0) {                                                                 \
+      long long _now = clock64();                                                    \
+      atomicAdd(&g_score_phase[k], (unsigned long long)(_now - _cp_t0));             \
+      _cp_t0 = _now;                                                                 \
+    }                                                                                \
+  } while (0)
+#define TW_CCOUNT(k, v) do { if (lane == 0) atomicAdd(&g_score_phase[k], (unsigned long long)(v)); } while (0)
+extern "C" int tw_debug_score_phases(unsigned long long* out24, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out24, g_score_phase, sizeof(unsigned long long) * 24);
+  if (e != cudaSuccess) return -2;
+  if (reset) {
+    unsigned long long z[24] = {0};
+    cudaMemcpyToSymbol(g_score_phase, z, sizeof z);
+  }
+  return 0;
+}
+#else
+#define TW_CPHASE(k) do { } while (0)
+#define TW_CCOUNT(k, v) do { } while (0)
+#endif
+
 #ifndef TW_S3_TBL
 #define TW_S3_TBL 320          // term-table slots per warp per round
 #define TW_S3_ENT 192          // feasible tuples per warp between two flushes of the list
@@ -50,6 +76,7 @@ constexpr int kS3Prm = TW_S3_PRM_TERMS * TW_MIX_REC;
 constexpr int kS3Warps = kS3Threads / 32;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kS3MaxR = 64;                 // candidates of one ep in one in-span's range
+constexpr int kS3RankMax = 12;              // segments up to this many feasible tuples are ranked entry-parallel
 constexpr long long kS3MaxP = 1LL << 24;    // combinations of one in-span
 
 // ---- PTX: mbarrier + 1-D bulk copy (TMA engine, SASS UBLKCP) ---------------------------------
@@ -122,9 +149,10 @@ struct S3Warp {
   int64_t ins[32], ine[32];
   alignas(16) uint32_t used[32][E][kNarrowW]; // candidate maps (V3:1043-1051)
   int seg_lo[32], seg_hi[32];
-  uint16_t val_slot[kS3Tbl];                  // compacted valid slots: slot index, term | batch << 6
-  uint8_t val_tid[kS3Tbl];
+  unsigned long long top_key[32][TW_K];       // quick ranking (2c): rank r of in-span j
+  typename S3Pack<E>::xp_t top_xp[32][TW_K];
   uint8_t ent_j[kS3Ent];
+  uint8_t seg_quick[32];
 };
 
 template <int E>
@@ -198,6 +226,9 @@ k_score3(tw_batch b, tw_params prm, int has_params, int keep_windows, tw_score_o
   using XP = typename S3Pack<E>::xp_t;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int t = blockIdx.x;
+#ifdef TW_PROFILE_PHASES
+  long long _cp_t0 = clock64();
+#endif
   if (keep_windows && overflow_flag[t]) return;      // the sequential kernel owns this tile
   const int p = tiles.tile_prob[t];
   const int i0 = tiles.tile_start[t];
@@ -289,6 +320,7 @@ k_score3(tw_batch b, tw_params prm, int has_params, int keep_windows, tw_score_o
   mbar_wait(&sm.bar, 0);
   __syncthreads();                                   // heads / tails / layout visible
 
+  TW_CPHASE(0);                                      // header, staging, barrier
   // ================= from here on the warps are independent =================
   const uint32_t* magic = sm.magic;
   // sink eps: the LAST term (V1:354-355) can only fall on an ep without DAG successors, unless end
@@ -335,6 +367,7 @@ k_score3(tw_batch b, tw_params prm, int has_params, int keep_windows, tw_score_o
   }
   const bool direct = tsize > kS3Tbl;        // tables do not fit: terms are evaluated per feasible tuple
 
+  TW_CPHASE(1);                                      // candidate ranges, table sizes
   // top-K of the own in-span: keys descending, 0 = empty
   unsigned long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0;
   XP tx0 = 0, tx1 = 0, tx2 = 0, tx3 = 0, tx4 = 0;
@@ -364,75 +397,80 @@ k_score3(tw_batch b, tw_params prm, int has_params, int keep_windows, tw_score_o
     const int cstart = cend - cneed;
     const int total_c = __shfl_sync(kFull, cend, 31);
 
-    // ---- 1a. slots: decode, validity, dt
-    int nval = 0;
-    for (int base = 0; base < total_t; base += 32) {
-      const int s = base + lane;
-      const bool act = s < total_t;
-      const int j = owner_of(tend, act ? s : total_t - 1);
-      const RP rpj = __shfl_sync(kFull, rp, j);
-      const S3Lo<E> lpj = lo_shfl<E>(lp, j);
-      const int loc = s - __shfl_sync(kFull, tstart, j);
-      int o = 0, tt = 0, e = 0, src = 0, re = 1;
-      for (; tt < n_terms; ++tt) {
-        e = sm.tep[tt];
-        src = sm.tsrc[tt];
-        re = r_get(rpj, e);
-        const int size = src >= 0 ? r_get(rpj, src) * re : (src == TW_TERM_ROOT || (sink >> e & 1u)) ? re : 0;
-        if (loc < o + size) break;
-        o += size;
-      }
-      bool valid = act && tt < n_terms;
-      double dt = 0.0;
-      if (valid) {
-        const int l = loc - o;
-        const int64_t je = ws.ine[j];
-        if (src >= 0) {
-          const int xb = (int)div_small((unsigned)l, re, magic), xe = l - xb * re;
-          const int pe = sm.woff_e[e] + lo_get<E>(lpj, e) + xe;
-          const int64_t eb = sm.st_e[sm.woff_e[src] + lo_get<E>(lpj, src) + xb];
-          const int64_t sv = sm.st_s[sm.woff_s[e] + lo_get<E>(lpj, e) + xe];
-          valid = eb <= je && sm.st_e[pe] <= je && eb <= sv;
-          dt = (double)(sv - eb);                                          // V1:345
-        } else {
-          const int pos = lo_get<E>(lpj, e) + l;
-          const int64_t en = sm.st_e[sm.woff_e[e] + pos];
-          valid = en <= je;
-          dt = src == TW_TERM_ROOT ? (double)(sm.st_s[sm.woff_s[e] + pos] - ws.ins[j])   // V1:349-350
-                                   : (double)(je - en);                               // V1:354-355
+    TW_CPHASE(2);                                    // admission
+    TW_CCOUNT(10, total_t);
+    TW_CCOUNT(11, total_c);
+    TW_CCOUNT(12, 1);
+    // ---- 1. term tables, TERM-MAJOR: for one term at a time the slots of all admitted in-spans are
+    // flattened over the warp, so the term, its eps, the candidate-count fields and (mixture pass)
+    // the likelihood record and its component count are warp-uniform: no per-slot term search, no
+    // divergence inside GetEpPairCost (V1:117-139), only live mixture components are evaluated.
+    // Slots no feasible tuple can use (containment / order fails) are never evaluated or read.
+    {
+      int o_run = tstart;                       // own table of the current term starts here
+      for (int tt = 0; tt < n_terms && total_t > 0; ++tt) {
+        const int e = sm.tep[tt], src = sm.tsrc[tt];
+        const bool tabled = src >= 0 || src == TW_TERM_ROOT || (sink >> e & 1u);
+        const int re_own = r_get(rp, e);
+        const int size = (admitted && !direct && tabled) ? (src >= 0 ? r_get(rp, src) * re_own : re_own) : 0;
+        int incl = size;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int o = __shfl_up_sync(kFull, incl, d);
+          if (lane >= d) incl += o;
         }
-      }
-      const unsigned m = __ballot_sync(kFull, valid);
-      if (valid) {
-        const int pos = nval + __popc(m & ((1u << lane) - 1u));
-        ws.tbl[s] = dt;
-        ws.val_slot[pos] = (uint16_t)s;
-        const int brel = prm.mode == TW_PARAMS_GAUSS_BATCHED ? (i0 + wid * 32 + j) / TW_PARAM_BATCH - batch0 : 0;
-        ws.val_tid[pos] = (uint8_t)(tt | (brel << 6));
-      }
-      nval += __popc(m);
-    }
-    __syncwarp();
-    // ---- 1b. values: GetEpPairCost (V1:117-139) of every valid slot
-    for (int base = 0; base < nval; base += 32) {
-      const int vi = base + lane;
-      if (vi < nval) {
-        const int s = ws.val_slot[vi];
-        const int id = ws.val_tid[vi];
-        ParamView pv;
-        pv.mode = prm.mode;
-        pv.gauss = prm_base + (id >> 6) * n_terms * TW_GAUSS_REC;
-        pv.mix = prm_base;
-        pv.etab = sm.etab;
-        ws.tbl[s] = term_logpdf(pv, id & 63, ws.tbl[s]);
+        const int total = __shfl_sync(kFull, incl, 31);
+        const int excl = incl - size;
+        const double* rec_mix = prm_base + tt * TW_MIX_REC;
+        for (int base = 0; base < total; base += 32) {
+          const int s = base + lane;
+          const bool act = s < total;
+          const int j = owner_of(incl, act ? s : total - 1);
+          const RP rpj = __shfl_sync(kFull, rp, j);
+          const S3Lo<E> lpj = lo_shfl<E>(lp, j);
+          const int l = s - __shfl_sync(kFull, excl, j);
+          const int tb = __shfl_sync(kFull, o_run, j);
+          const int re = r_get(rpj, e);
+          const int64_t je = ws.ine[j];
+          bool valid = act;
+          double dt = 0.0;
+          if (src >= 0) {
+            const int xb = (int)div_small((unsigned)l, re, magic), xe = l - xb * re;
+            const int64_t eb = sm.st_e[sm.woff_e[src] + lo_get<E>(lpj, src) + xb];
+            const int pe = lo_get<E>(lpj, e) + xe;
+            const int64_t sv = sm.st_s[sm.woff_s[e] + pe];
+            valid = valid && eb <= je && sm.st_e[sm.woff_e[e] + pe] <= je && eb <= sv;
+            dt = (double)(sv - eb);                                              // V1:345
+          } else {
+            const int pos = lo_get<E>(lpj, e) + l;
+            const int64_t en = sm.st_e[sm.woff_e[e] + pos];
+            valid = valid && en <= je;
+            dt = src == TW_TERM_ROOT ? (double)(sm.st_s[sm.woff_s[e] + pos] - ws.ins[j])   // V1:349-350
+                                     : (double)(je - en);                               // V1:354-355
+          }
+          TW_CCOUNT(14, __popc(__ballot_sync(kFull, valid)));
+          if (valid) {
+            double val;
+            if (prm.mode == TW_PARAMS_GAUSS_BATCHED) {
+              const int brel = (i0 + wid * 32 + j) / TW_PARAM_BATCH - batch0;
+              val = gauss_logpdf(prm_base + (brel * n_terms + tt) * TW_GAUSS_REC, dt);
+            } else {
+              val = mix_logpdf_tab_uniform(rec_mix, dt, sm.etab);
+            }
+            ws.tbl[tb + l] = val;
+          }
+        }
+        o_run += size;
       }
     }
     __syncwarp();
 
+    TW_CPHASE(3);                                    // term tables
     // ---- 2. combinations, in chunks of the entry list
     int n_ent = 0;
     int base = 0;
     while (true) {
+      const int chunk_base = base;
       // 2a. feasibility (V3:328-347) -> compacted (tuple, owner) list, in DFS leaf order per owner
       for (; base < total_c && n_ent <= kS3Ent - 32; base += 32) {
         const int g = base + lane;
@@ -484,6 +522,8 @@ k_score3(tw_batch b, tw_params prm, int has_params, int keep_windows, tw_score_o
         n_ent += __popc(m);
       }
       __syncwarp();
+      TW_CPHASE(4);                                  // 2a feasibility
+      TW_CCOUNT(13, n_ent);
       // 2b. scores: sum of table entries in the reference's term order (V1:316-357)
       if (has_params) {
         for (int eb = 0; eb < n_ent; eb += 32) {
@@ -504,9 +544,10 @@ k_score3(tw_batch b, tw_params prm, int has_params, int keep_windows, tw_score_o
               ce[e] = sm.st_e[sm.woff_e[e] + lo_get<E>(lpj, e) + x[e]];
             }
             int last = 0;                       // max(..., key=end) keeps the first maximum (V1:314)
+            int64_t last_end = ce[0];
 #pragma unroll
             for (int e = 1; e < E; ++e)
-              if (ce[e] > ce[last]) last = e;
+              if (ce[e] > last_end) { last_end = ce[e]; last = e; }
             const int brel = prm.mode == TW_PARAMS_GAUSS_BATCHED ? (i0 + wid * 32 + j) / TW_PARAM_BATCH - batch0 : 0;
             double cost = 0.0;
             int o = tstj;
@@ -542,6 +583,7 @@ k_score3(tw_batch b, tw_params prm, int has_params, int keep_windows, tw_score_o
         }
         __syncwarp();
       }
+      TW_CPHASE(5);                                  // 2b scores
       // 2c. per-owner segments of the list (entries are grouped by owner, in leaf order)
       ws.seg_lo[lane] = 0;
       ws.seg_hi[lane] = 0;
@@ -552,11 +594,47 @@ k_score3(tw_batch b, tw_params prm, int has_params, int keep_windows, tw_score_o
         if (en == n_ent - 1 || ws.ent_j[en + 1] != j) ws.seg_hi[j] = en + 1;
       }
       __syncwarp();
-      {
-        const int a = ws.seg_lo[lane], z = ws.seg_hi[lane];
-        nfeas += z - a;
-        if (has_params) {
-          for (int en = a; en < z; ++en) {
+      const int sa = ws.seg_lo[lane], sz = ws.seg_hi[lane];
+      nfeas += sz - sa;
+      if (has_params) {
+        // An in-span whose combinations all fell into this chunk (the rule) and whose segment is
+        // short is ranked by its ENTRIES in parallel: entry en counts the larger keys of its segment
+        // and, if fewer than K, writes itself to that rank.  Equal keys / NaN -> the tile is redone.
+        const bool whole = cneed > 0 && cstart >= chunk_base && cend <= base;
+        const bool quick = whole && sz - sa <= kS3RankMax;
+        ws.seg_quick[lane] = (uint8_t)quick;
+        __syncwarp();
+        bool bad = false;
+        for (int en = lane; en < n_ent; en += 32) {
+          const int j = ws.ent_j[en];
+          if (!ws.seg_quick[j]) continue;
+          const unsigned long long k = ws.ent_key[en];
+          const int a = ws.seg_lo[j], z = ws.seg_hi[j];
+          int rank = 0;
+          bool tie = k == 0ull;
+          for (int q = a; q < z; ++q) {
+            const unsigned long long o = ws.ent_key[q];
+            rank += o > k;
+            tie = tie || (o == k && q != en);
+          }
+          bad = bad || tie;
+          if (rank < TW_K) {
+            ws.top_key[j][rank] = k;
+            ws.top_xp[j][rank] = ws.ent_xp[en];
+          }
+        }
+        redo = redo || bad;
+        __syncwarp();
+        if (quick) {
+          const int len = sz - sa;
+          tk0 = len > 0 ? ws.top_key[lane][0] : 0ull; tx0 = len > 0 ? ws.top_xp[lane][0] : (XP)0;
+          tk1 = len > 1 ? ws.top_key[lane][1] : 0ull; tx1 = len > 1 ? ws.top_xp[lane][1] : (XP)0;
+          tk2 = len > 2 ? ws.top_key[lane][2] : 0ull; tx2 = len > 2 ? ws.top_xp[lane][2] : (XP)0;
+          tk3 = len > 3 ? ws.top_key[lane][3] : 0ull; tx3 = len > 3 ? ws.top_xp[lane][3] : (XP)0;
+          tk4 = len > 4 ? ws.top_key[lane][4] : 0ull; tx4 = len > 4 ? ws.top_xp[lane][4] : (XP)0;
+        } else {
+          // long or streamed segments: the owner lane walks its segment; 5 keys in registers
+          for (int en = sa; en < sz; ++en) {
             unsigned long long k = ws.ent_key[en];
             if (k == 0ull) { redo = true; continue; }      // NaN score: the reference's order decides
             if (k < tk4) continue;
@@ -572,6 +650,7 @@ k_score3(tw_batch b, tw_params prm, int has_params, int keep_windows, tw_score_o
         }
       }
       __syncwarp();
+      TW_CPHASE(6);                                  // 2c top-K
       n_ent = 0;
       if (base >= total_c) break;
     }
@@ -582,6 +661,7 @@ k_score3(tw_batch b, tw_params prm, int has_params, int keep_windows, tw_score_o
     return;
   }
 
+  TW_CPHASE(2);
   // ================= results, staged through shared memory =================
   const int w0 = wid * 32;
   const int nv = min(32, cnt - w0);            // in-spans of this warp
@@ -636,6 +716,7 @@ k_score3(tw_batch b, tw_params prm, int has_params, int keep_windows, tw_score_o
     warp_copy_out(out.used_bits + 2 * tb, &ws.used[0][0][0], nv * E * kNarrowW, lane);
     if (worker) out.used_wide[g0 + lane] = 0;
   }
+  TW_CPHASE(7);                                      // results
 }
 
 // ---------------------------------------------------------------------------------------------

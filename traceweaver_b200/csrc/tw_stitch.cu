@@ -115,7 +115,12 @@ __device__ __forceinline__ bool stitch_small_window(StitchWarpSmem& sm, int E, i
       if ((comp >> a) & 1u) space *= cnt[a] + 1;
     }
     if (space > kSmallSpace) return false;
+    // One pass: every lane keeps (largest total seen, first leaf tied with it) over its leaves, the
+    // warp then merges the pairs.  Totals are either tied (equal up to rounding, far below
+    // TW_MWIS_TIE_TOL) or apart by more than the tolerance, so "first leaf tied with the maximum"
+    // is what the sequential search returns, whatever the order in which totals were rounded.
     double best_w = -1.0;
+    int best_idx = 0x7fffffff;
     for (int idx = lane; idx < space; idx += 32) {
       int rem = idx;
       uint32_t sel = 0u;
@@ -135,41 +140,20 @@ __device__ __forceinline__ bool stitch_small_window(StitchWarpSmem& sm, int E, i
           }
         }
       }
-      if (ok && tot > best_w) best_w = tot;
+      if (ok) {
+        if (tot > best_w + TW_MWIS_TIE_TOL) { best_w = tot; best_idx = idx; }   // a better group
+        else if (tot > best_w) best_w = tot;                                    // same group: keep the first leaf
+      }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
       const double ow = __shfl_xor_sync(kAll, best_w, d);
-      best_w = ow > best_w ? ow : best_w;
-    }
-    // the first leaf (lowest index) whose total is tied with the maximum (TW_MWIS_TIE_TOL): what the
-    // sequential search returns, whatever the order in which the totals were rounded
-    int best_idx = 0x7fffffff;
-    for (int idx = lane; idx < space && best_idx == 0x7fffffff; idx += 32) {
-      int rem = idx;
-      uint32_t sel = 0u;
-      double tot = 0.0;
-      bool ok = true;
-#pragma unroll
-      for (int a = 0; a < kSmallWindow; ++a) {
-        if ((comp >> a) & 1u) {
-          const int d = rem / stride[a];
-          rem -= d * stride[a];
-          if (d < cnt[a]) {
-            const int c = TW_K * a + d;
-            const double wgt = sm.cw[c];
-            if (!(wgt > 0.0) || (sm.cconf[c] & sel)) ok = false;
-            sel |= 1u << c;
-            tot = tot + wgt;
-          }
-        }
-      }
-      if (ok && tot >= best_w - TW_MWIS_TIE_TOL) best_idx = idx;
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
       const int oi = __shfl_xor_sync(kAll, best_idx, d);
-      best_idx = oi < best_idx ? oi : best_idx;
+      if (ow > best_w + TW_MWIS_TIE_TOL) { best_w = ow; best_idx = oi; }
+      else if (!(best_w > ow + TW_MWIS_TIE_TOL)) {      // tied groups: the earlier leaf, the larger total
+        best_idx = oi < best_idx ? oi : best_idx;
+        best_w = ow > best_w ? ow : best_w;
+      }
     }
     {
       int rem = best_idx;
