@@ -22,6 +22,8 @@ TW_PARAMS_GAUSS_BATCHED = 0
 TW_PARAMS_MIXTURE = 1
 
 TW_OK = 0
+TW_ERR_INVALID, TW_ERR_CUDA, TW_ERR_MWIS_LIMIT, TW_ERR_RANGE_LIMIT, TW_ERR_UNSUPPORTED, TW_ERR_NO_DEVICE = \
+    -1, -2, -3, -4, -5, -6
 STATUS = {0: "TW_OK", -1: "TW_ERR_INVALID", -2: "TW_ERR_CUDA", -3: "TW_ERR_MWIS_LIMIT",
           -4: "TW_ERR_RANGE_LIMIT", -5: "TW_ERR_UNSUPPORTED", -6: "TW_ERR_NO_DEVICE"}
 

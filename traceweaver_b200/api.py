@@ -98,9 +98,15 @@ class BatchSolver:
         edges = sorted(set([0, hb.n_problems] + [int(c) for c in cuts if 0 < c < hb.n_problems]))
         return [(lo, hi, hb.slice(lo, hi)) for lo, hi in zip(edges[:-1], edges[1:])]
 
-    def solve(self, hb: HostBatch, truth_assign=None, term_order=None, want_scores=False):
+    def solve(self, hb: HostBatch, truth_assign=None, term_order=None, want_scores=False, strict=True):
         """want_scores: also return out["topk_score"] (float64 [sum n_in, 5]; the reference's 6-tuple
-        carries the top-K ids only, traceweaver_v3.py:1229, so the scores stay on the device by default)."""
+        carries the top-K ids only, traceweaver_v3.py:1229, so the scores stay on the device by default).
+
+        strict=False: a service that runs into a search limit of the engine (TW_ERR_MWIS_LIMIT: more
+        than 2 M branch-and-bound nodes in one window) no longer fails the whole call: the other
+        services' results are returned, out["counters"][p, 3] holds the status of service p (0 = ok;
+        the in-spans of a failed service after the failing window stay unassigned) and
+        out["failed_services"] lists the failed ones.  Anything else still raises."""
         dev = self.engine.device
         self._flip ^= 1
         single = truth_assign is not None or term_order is not None
@@ -171,9 +177,18 @@ class BatchSolver:
                     d2h += t.numel() * t.element_size()
             used.append((eng, stream))
         self._copy_stream.synchronize()
+        limit_hit = False
         for eng, stream in dict((id(e), (e, s)) for e, s in used).values():
             with torch.cuda.stream(stream):
-                eng.status()                                      # syncs the stream, raises on engine errors
+                try:
+                    eng.status()                                  # syncs the stream, raises on engine errors
+                except _abi.TwError as ex:
+                    if strict or ex.code != _abi.TW_ERR_MWIS_LIMIT:
+                        raise
+                    limit_hit = True
             main.wait_stream(stream)
         self.h2d_bytes, self.d2h_bytes = h2d, d2h
-        return {k: v.numpy() for k, v in out.items()}
+        res = {k: v.numpy() for k, v in out.items()}
+        if not strict:
+            res["failed_services"] = np.flatnonzero(res["counters"][:, 3] != 0) if limit_hit else np.zeros(0, np.int64)
+        return res

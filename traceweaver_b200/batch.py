@@ -68,12 +68,27 @@ class Problem:
             for b in self.preds[e]:
                 if not (0 <= b < e):
                     raise ValueError(f"{self.name}: preds must reference earlier topological positions")
+        if len(self.out_end) != E or len(self.preds) != E:
+            raise ValueError(f"{self.name}: out_start / out_end / preds must have one entry per ep")
+        if self.in_end.shape != self.in_start.shape:
+            raise ValueError(f"{self.name}: in_start and in_end differ in length")
+        if np.any(self.in_end < self.in_start):
+            raise ValueError(f"{self.name}: an in-span ends before it starts")
         key = self.in_start.astype(np.int64)
         if np.any(np.diff(key) < 0):
             raise ValueError(f"{self.name}: in-spans not sorted by start")
         for e in range(E):
+            if self.out_end[e].shape != self.out_start[e].shape:
+                raise ValueError(f"{self.name}: out_start and out_end of ep {e} differ in length")
+            if np.any(self.out_end[e] < self.out_start[e]):
+                raise ValueError(f"{self.name}: an out-span of ep {e} ends before it starts")
             if np.any(np.diff(self.out_start[e]) < 0):
                 raise ValueError(f"{self.name}: out-spans of ep {e} not sorted by start")
+
+    def in_accelerated_regime(self):
+        """True iff every ep has as many outgoing spans as there are incoming ones (no skip budget,
+        traceweaver_v3.py:1138-1158): the regime the engine solves."""
+        return all(len(o) == self.n_in for o in self.out_start)
 
 
 @dataclass

@@ -149,6 +149,7 @@ struct S3Warp {
   int64_t ins[32], ine[32];
   alignas(16) uint32_t used[32][E][kNarrowW]; // candidate maps (V3:1043-1051)
   int seg_lo[32], seg_hi[32];
+  uint16_t val_slot[kS3Tbl];                  // compacted valid slots of the current term: slot | batch << 12
   unsigned long long top_key[32][TW_K];       // quick ranking (2c): rank r of in-span j
   typename S3Pack<E>::xp_t top_xp[32][TW_K];
   uint8_t ent_j[kS3Ent];
@@ -422,6 +423,7 @@ k_score3(tw_batch b, tw_params prm, int has_params, int keep_windows, tw_score_o
         const int total = __shfl_sync(kFull, incl, 31);
         const int excl = incl - size;
         const double* rec_mix = prm_base + tt * TW_MIX_REC;
+        int nv = 0;
         for (int base = 0; base < total; base += 32) {
           const int s = base + lane;
           const bool act = s < total;
@@ -448,18 +450,33 @@ k_score3(tw_batch b, tw_params prm, int has_params, int keep_windows, tw_score_o
             dt = src == TW_TERM_ROOT ? (double)(sm.st_s[sm.woff_s[e] + pos] - ws.ins[j])   // V1:349-350
                                      : (double)(je - en);                               // V1:354-355
           }
-          TW_CCOUNT(14, __popc(__ballot_sync(kFull, valid)));
+          // valid slots are compacted so that the FP64 work below runs on full warps
+          const unsigned vm = __ballot_sync(kFull, valid);
+          TW_CCOUNT(14, __popc(vm));
           if (valid) {
+            const int pos = nv + __popc(vm & ((1u << lane) - 1u));
+            const int brel = prm.mode == TW_PARAMS_GAUSS_BATCHED ? (i0 + wid * 32 + j) / TW_PARAM_BATCH - batch0 : 0;
+            ws.tbl[tb + l] = dt;
+            ws.val_slot[pos] = (uint16_t)((tb + l) | (brel << 12));
+          }
+          nv += __popc(vm);
+        }
+        __syncwarp();
+        for (int vb = 0; vb < nv; vb += 32) {
+          const int vi = vb + lane;
+          if (vi < nv) {
+            const int code = ws.val_slot[vi];
+            const int slot = code & 0xfff;
+            const double dt = ws.tbl[slot];
             double val;
-            if (prm.mode == TW_PARAMS_GAUSS_BATCHED) {
-              const int brel = (i0 + wid * 32 + j) / TW_PARAM_BATCH - batch0;
-              val = gauss_logpdf(prm_base + (brel * n_terms + tt) * TW_GAUSS_REC, dt);
-            } else {
+            if (prm.mode == TW_PARAMS_GAUSS_BATCHED)
+              val = gauss_logpdf(prm_base + ((code >> 12) * n_terms + tt) * TW_GAUSS_REC, dt);
+            else
               val = mix_logpdf_tab_uniform(rec_mix, dt, sm.etab);
-            }
-            ws.tbl[tb + l] = val;
+            ws.tbl[slot] = val;
           }
         }
+        __syncwarp();
         o_run += size;
       }
     }
@@ -632,21 +649,58 @@ k_score3(tw_batch b, tw_params prm, int has_params, int keep_windows, tw_score_o
           tk2 = len > 2 ? ws.top_key[lane][2] : 0ull; tx2 = len > 2 ? ws.top_xp[lane][2] : (XP)0;
           tk3 = len > 3 ? ws.top_key[lane][3] : 0ull; tx3 = len > 3 ? ws.top_xp[lane][3] : (XP)0;
           tk4 = len > 4 ? ws.top_key[lane][4] : 0ull; tx4 = len > 4 ? ws.top_xp[lane][4] : (XP)0;
-        } else {
-          // long or streamed segments: the owner lane walks its segment; 5 keys in registers
-          for (int en = sa; en < sz; ++en) {
+        }
+        // long or streamed segments, one at a time by the WHOLE warp: every lane keeps the top K of
+        // the entries a + lane, a + lane + 32, ... (the owner lane starts from its running list), then
+        // K rounds of "largest head over the lanes" give the segment's top K to the owner.
+        unsigned slow = __ballot_sync(kFull, !quick && sz > sa);
+        while (slow) {
+          const int j = __ffs(slow) - 1;
+          slow &= slow - 1u;
+          const int a = __shfl_sync(kFull, sa, j), z = __shfl_sync(kFull, sz, j);
+          const bool own = lane == j;
+          unsigned long long l0 = own ? tk0 : 0ull, l1 = own ? tk1 : 0ull, l2 = own ? tk2 : 0ull,
+                             l3 = own ? tk3 : 0ull, l4 = own ? tk4 : 0ull;
+          XP y0 = own ? tx0 : (XP)0, y1 = own ? tx1 : (XP)0, y2 = own ? tx2 : (XP)0, y3 = own ? tx3 : (XP)0,
+             y4 = own ? tx4 : (XP)0;
+          bool bad = false;
+          for (int en = a + lane; en < z; en += 32) {
             unsigned long long k = ws.ent_key[en];
-            if (k == 0ull) { redo = true; continue; }      // NaN score: the reference's order decides
-            if (k < tk4) continue;
+            if (k == 0ull) { bad = true; continue; }        // NaN score: the reference's order decides
+            if (k < l4) continue;
             XP xq = ws.ent_xp[en];
-            // compare-exchange down the list; equal keys -> the reference's tie order decides
-            redo = redo || k == tk0 || k == tk1 || k == tk2 || k == tk3 || k == tk4;
+            bad = bad || k == l0 || k == l1 || k == l2 || k == l3 || k == l4;   // equal keys: tie order
 #define TW_S3_CE(K, X)                                              \
   if (k > K) { const unsigned long long tkk = K; K = k; k = tkk;    \
                const XP txx = X; X = xq; xq = txx; }
-            TW_S3_CE(tk0, tx0) TW_S3_CE(tk1, tx1) TW_S3_CE(tk2, tx2) TW_S3_CE(tk3, tx3) TW_S3_CE(tk4, tx4)
+            TW_S3_CE(l0, y0) TW_S3_CE(l1, y1) TW_S3_CE(l2, y2) TW_S3_CE(l3, y3) TW_S3_CE(l4, y4)
 #undef TW_S3_CE
           }
+          unsigned long long n0 = 0, n1 = 0, n2 = 0, n3 = 0, n4 = 0;
+          XP m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0;
+#pragma unroll
+          for (int r = 0; r < TW_K; ++r) {
+            const uint32_t hi = (uint32_t)(l0 >> 32);
+            const uint32_t mh = __reduce_max_sync(kFull, hi);
+            const uint32_t lo32 = hi == mh ? (uint32_t)l0 : 0u;
+            const uint32_t ml = __reduce_max_sync(kFull, lo32);
+            const unsigned long long key = ((unsigned long long)mh << 32) | ml;
+            const unsigned win = __ballot_sync(kFull, key != 0ull && l0 == key);
+            if (__popc(win) > 1) bad = true;                 // the same key twice: tie order
+            const int wl = win ? __ffs(win) - 1 : 0;
+            const XP xw = __shfl_sync(kFull, y0, wl);
+            if (r == 0) { n0 = key; m0 = xw; }
+            if (r == 1) { n1 = key; m1 = xw; }
+            if (r == 2) { n2 = key; m2 = xw; }
+            if (r == 3) { n3 = key; m3 = xw; }
+            if (r == 4) { n4 = key; m4 = xw; }
+            if (win && lane == wl) { l0 = l1; l1 = l2; l2 = l3; l3 = l4; l4 = 0ull; y0 = y1; y1 = y2; y2 = y3; y3 = y4; }
+          }
+          if (own) {
+            tk0 = n0; tk1 = n1; tk2 = n2; tk3 = n3; tk4 = n4;
+            tx0 = m0; tx1 = m1; tx2 = m2; tx3 = m3; tx4 = m4;
+          }
+          redo = redo || bad;
         }
       }
       __syncwarp();
@@ -684,6 +738,7 @@ k_score3(tw_batch b, tw_params prm, int has_params, int keep_windows, tw_score_o
     // indices: lanes in groups that fit the staging area
     constexpr int kPer = TW_K * E;                       // ints per in-span
     constexpr int kGroup = (kS3Tbl * 2) / kPer >= 32 ? 32 : 16;
+    static_assert(kS3Tbl <= 4096, "val_slot packs the slot index into 12 bits");
     static_assert((kS3Tbl * 2) / kPer >= 16, "staging area too small for the index block");
     int* si = reinterpret_cast<int*>(ws.tbl);
     int32_t* gidx = out.topk_idx + TW_K * (tuple_off + (int64_t)(i0 + w0) * E);

@@ -333,9 +333,19 @@ def _service_problem(process, i_rows: _Rows, o_rows: _Rows) -> Optional[ServiceP
         truth=np.ascontiguousarray(truth_given[g_of]), graph_edges=list(G.edges()))
 
 
-def to_host_batch(services: Sequence[ServiceProblem]):
-    """One bindable batch for all services that are in the accelerated regime (n_out == n_in)."""
-    return build_batch([s.problem for s in services])
+def to_host_batch(services: Sequence[ServiceProblem], skipped: list = None):
+    """One bindable batch of the services that are in the accelerated regime (every callee list as
+    long as the incoming list, i.e. no skip budget, traceweaver_v3.py:1138-1158).  Services outside it
+    are left out — one of them would make tw_engine_bind reject the whole batch — and appended to
+    `skipped` when the caller passes a list; the order of the others is kept.  Returns None when no
+    service qualifies."""
+    keep = []
+    for s in services:
+        if s.problem.in_accelerated_regime():
+            keep.append(s)
+        elif skipped is not None:
+            skipped.append(s)
+    return build_batch([s.problem for s in keep]) if keep else None
 
 
 def accuracy(service: ServiceProblem, assign: np.ndarray) -> float:
