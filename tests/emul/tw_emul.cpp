@@ -277,7 +277,7 @@ extern "C" int twe_assign_window(int nw, const int* cnt, const double* score, co
     member[k] = k;
     for (int r = 0; r < cnt[k]; ++r) { wb->score[k][r] = score[k * TW_K + r]; wb->idx[k][r][0] = span[k * TW_K + r]; }
   }
-  assignment_solve(*wb, member, nw, chosen);
+  assignment_solve(*wb, member, nw, 0, chosen, nullptr, nullptr);
   delete wb;
   return 0;
 }

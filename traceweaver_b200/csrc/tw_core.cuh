@@ -781,7 +781,14 @@ TW_HD uint32_t window_adjacency(const WindowBuf& wb, int E, int nw, int k) {
 // column per in-span) instead of branch and bound, whose search explodes when ~30 in-spans compete
 // for interchangeable spans.  Same optimum as the MWIS formulation of V3:1252-1274.
 #define TW_ASSIGN_MAX_COLS (TW_WINDOW_CAP * (TW_K + 1) + 1)
-TW_HD_NOINLINE inline void assignment_solve(const WindowBuf& wb, const int* member, int m, int* best) {
+constexpr int kMwisPricedMin = 7;   // components of at least this many in-spans get the priced bound
+// `pos`: tuple position whose spans are the columns (E = 1: position 0 is the whole problem; E > 1: the
+// projection of the window on one callee, a RELAXATION whose dual prices bound the branch and bound
+// below).  best != nullptr: the matching (first tied optimum); price != nullptr: the dual price of
+// every candidate's column and their total (a candidate's weight never exceeds its row's dual plus
+// its column's price; prices are >= 0).
+TW_HD_NOINLINE inline void assignment_solve(const WindowBuf& wb, const int* member, int m, int pos, int* best,
+                                            double (*price)[TW_K], double* price_total) {
   // columns 1..ncol: distinct out spans; ncol+1..ncol+m: "row l stays unassigned"
   int colid[TW_WINDOW_CAP * TW_K];
   int ncol = 0;
@@ -791,7 +798,7 @@ TW_HD_NOINLINE inline void assignment_solve(const WindowBuf& wb, const int* memb
     for (int r = 0; r < TW_K; ++r) {
       ecol[l][r] = -1;
       if (r >= wb.cnt[k] || !(TW_WEIGHT_OFFSET + wb.score[k][r] > 0.0)) continue;
-      const int span = wb.idx[k][r][0];
+      const int span = wb.idx[k][r][pos];
       int j = 0;
       while (j < ncol && colid[j] != span) ++j;
       if (j == ncol) colid[ncol++] = span;
@@ -844,6 +851,14 @@ TW_HD_NOINLINE inline void assignment_solve(const WindowBuf& wb, const int* memb
       j0 = j1;
     } while (j0);
   }
+  if (price) {
+    double tot = 0.0;
+    for (int j = 1; j <= ncol; ++j) tot += -vv[j];
+    *price_total = tot;
+    for (int l = 0; l < m; ++l)
+      for (int r = 0; r < TW_K; ++r) price[l][r] = ecol[l][r] >= 1 ? -vv[ecol[l][r]] : 0.0;
+  }
+  if (!best) return;
   // ---- tied optima (TW_MWIS_TIE_TOL): the canonical answer is the FIRST optimal solution in the
   // depth-first order of the branch and bound (in-spans ascending; ranks ascending, "unassigned"
   // last).  Every optimal matching lives in the equality subgraph of the final potentials (edges
@@ -960,21 +975,77 @@ TW_HD_NOINLINE inline long long mwis_solve(WindowBuf& wb, int E, int nw, long lo
     }
     if (E == 1 && m >= 3) {   // bipartite case: exact matching in polynomial time
       int bst[TW_WINDOW_CAP];
-      assignment_solve(wb, member, m, bst);
+      assignment_solve(wb, member, m, 0, bst, nullptr, nullptr);
       for (int l = 0; l < m; ++l) wb.chosen[member[l]] = bst[l];
       nodes += m;
       continue;
     }
-    double ub[TW_WINDOW_CAP + 1];
-    ub[m] = 0.0;
-    for (int l = m - 1; l >= 0; --l) {
-      int k = member[l];
-      double mx = 0.0;
-      for (int r = 0; r < wb.cnt[k]; ++r) {
-        double w = TW_WEIGHT_OFFSET + wb.score[k][r];
-        if (w > mx) mx = w;
+    // Depth-first branch and bound over the component's in-spans in window order ("rank r", ranks
+    // ascending, then "unassigned").  avail[L][j] = ranks of in-span j (j >= L) that are still
+    // compatible with the choices made at levels < L; the bound of a node is the sum over the
+    // remaining in-spans of their best AVAILABLE weight (lists are sorted by score, so that is the
+    // lowest available rank).  Compared with the static sum of maxima this cuts the search of windows
+    // in which ~30 in-spans compete for interchangeable spans by orders of magnitude; the optimum and
+    // the tie rule (first tied leaf in this order, TW_MWIS_TIE_TOL) are unchanged.
+    uint8_t avail[TW_WINDOW_CAP + 1][TW_WINDOW_CAP];
+    double rem[TW_WINDOW_CAP + 1];                 // plain bound of the in-spans L..m-1 given avail[L]
+    // Large components: second bound from the dual prices of ONE callee's assignment relaxation (every
+    // out span of that callee serves at most one in-span): sum over the remaining in-spans of their
+    // best available REDUCED weight (weight - price of its span, floored at 0) + the prices not yet
+    // spent.  At the root this equals the relaxation's optimum — far below the sum of maxima when the
+    // in-spans compete for the same spans — and it stays valid at every node for any prices >= 0.
+    double price[TW_WINDOW_CAP][TW_K];
+    double remp[TW_WINDOW_CAP + 1], lam[TW_WINDOW_CAP + 1];
+    const bool priced = m >= kMwisPricedMin;
+    if (priced) {
+      int pos = 0, fewest = 0x7fffffff;           // the callee with the fewest distinct spans: most competition
+      for (int e = 0; e < E; ++e) {
+        int distinct = 0;
+        for (int l = 0; l < m; ++l)
+          for (int r = 0; r < wb.cnt[member[l]]; ++r) {
+            const int sp = wb.idx[member[l]][r][e];
+            bool seen = false;
+            for (int l2 = 0; l2 <= l && !seen; ++l2)
+              for (int r2 = 0; r2 < (l2 < l ? wb.cnt[member[l2]] : r) && !seen; ++r2)
+                seen = wb.idx[member[l2]][r2][e] == sp;
+            distinct += !seen;
+          }
+        if (distinct < fewest) { fewest = distinct; pos = e; }
       }
-      ub[l] = ub[l + 1] + mx;
+      assignment_solve(wb, member, m, pos, nullptr, price, &lam[0]);
+      nodes += m;
+    } else {
+      lam[0] = 0.0;
+      for (int l = 0; l < m; ++l)
+        for (int r = 0; r < TW_K; ++r) price[l][r] = 0.0;
+    }
+    auto best_avail = [&](int j, uint8_t mask) {
+      if (!mask) return 0.0;
+      int r = 0;
+      while (!(mask >> r & 1u)) ++r;
+      return TW_WEIGHT_OFFSET + wb.score[member[j]][r];
+    };
+    auto best_reduced = [&](int j, uint8_t mask) {
+      double mx = 0.0;
+      for (int r = 0; r < TW_K; ++r)
+        if (mask >> r & 1u) {
+          const double v = TW_WEIGHT_OFFSET + wb.score[member[j]][r] - price[j][r];
+          mx = v > mx ? v : mx;
+        }
+      return mx;
+    };
+    rem[0] = 0.0;
+    remp[0] = 0.0;
+    for (int l = 0; l < m; ++l) {
+      const int k = member[l];
+      uint8_t mask = 0;
+      for (int r = 0; r < wb.cnt[k]; ++r)
+        if (TW_WEIGHT_OFFSET + wb.score[k][r] > 0.0) mask |= (uint8_t)(1u << r);
+      avail[0][l] = mask;
+    }
+    for (int l = m - 1; l >= 0; --l) {
+      rem[0] += best_avail(l, avail[0][l]);
+      remp[0] += best_reduced(l, avail[0][l]);
     }
     int choice[TW_WINDOW_CAP], best[TW_WINDOW_CAP], iter[TW_WINDOW_CAP + 1];
     double cur[TW_WINDOW_CAP + 1];
@@ -993,31 +1064,51 @@ TW_HD_NOINLINE inline long long mwis_solve(WindowBuf& wb, int E, int nw, long lo
         --level;
         continue;
       }
-      int k = member[level];
+      const int k = member[level];
       if (iter[level] == 0) {
         ++nodes;
         if (node_limit > 0 && nodes > node_limit) return -1;
-        if (cur[level] + ub[level] <= best_w + TW_MWIS_TIE_TOL) { --level; continue; }
+        double bound = rem[level];
+        if (priced) {
+          // (a few ulps of slack: the priced bound is assembled from differences of large numbers)
+          const double bp = remp[level] + lam[level] + 1e-7;
+          bound = bp < bound ? bp : bound;
+        }
+        if (cur[level] + bound <= best_w + TW_MWIS_TIE_TOL) { --level; continue; }
       }
-      int r = iter[level]++;
+      const int r = iter[level]++;
       if (r > wb.cnt[k]) { --level; continue; }
       if (r == wb.cnt[k]) {  // leave in-span k unassigned
         choice[level] = -1;
         cur[level + 1] = cur[level];
+        for (int j = level + 1; j < m; ++j) avail[level + 1][j] = avail[level][j];
+        rem[level + 1] = rem[level] - best_avail(level, avail[level][level]);
+        remp[level + 1] = remp[level] - best_reduced(level, avail[level][level]);
+        lam[level + 1] = lam[level];
         ++level;
         iter[level] = 0;
         continue;
       }
-      double w = TW_WEIGHT_OFFSET + wb.score[k][r];
-      if (!(w > 0.0)) continue;
-      bool ok = true;
-      for (int l = 0; l < level && ok; ++l)
-        if (choice[l] >= 0 && (wb.adj[k] >> member[l] & 1u) &&
-            tuples_conflict(wb.idx[k][r], wb.idx[member[l]][choice[l]], E))
-          ok = false;
-      if (!ok) continue;
+      if (!(avail[level][level] >> r & 1u)) continue;      // weight <= 0, or taken by an earlier choice
+      const double w = TW_WEIGHT_OFFSET + wb.score[k][r];
+      // the choice closes the conflicting ranks of the later in-spans
+      double rest = 0.0, restp = 0.0;
+      for (int j = level + 1; j < m; ++j) {
+        uint8_t mask = avail[level][j];
+        if (mask && (wb.adj[k] >> member[j] & 1u)) {
+          const int kj = member[j];
+          for (int q = 0; q < wb.cnt[kj]; ++q)
+            if ((mask >> q & 1u) && tuples_conflict(wb.idx[k][r], wb.idx[kj][q], E)) mask &= (uint8_t)~(1u << q);
+        }
+        avail[level + 1][j] = mask;
+        rest += best_avail(j, mask);
+        if (priced) restp += best_reduced(j, mask);
+      }
       choice[level] = r;
       cur[level + 1] = cur[level] + w;
+      rem[level + 1] = rest;
+      remp[level + 1] = restp;
+      lam[level + 1] = lam[level] - price[level][r];
       ++level;
       iter[level] = 0;
     }

@@ -255,6 +255,26 @@ k_score3(tw_batch b, tw_params prm, int has_params, int keep_windows, tw_score_o
     return;
   }
   if (tid == 0) mbar_init(&sm.bar, 2 * E);
+  __syncthreads();                                   // mbarrier initialised
+
+  // ---- bulk copies: thread 2e stages the start times of ep e, thread 2e+1 the end times
+  if (tid < 2 * E) {
+    const int e = tid >> 1, which = tid & 1;
+    int off = 0;
+    for (int q = 0; q < e; ++q) off += (tw[2 * q + 1] + 3) & ~1;
+    const int a = tw[2 * e], ne = tw[2 * e + 1];
+    const int64_t* g = (which ? b.out_end : b.out_start) + b.ep_out_off[ep0 + e] + a;
+    const int mis = (int)((((uintptr_t)g) >> 3) & 1u);
+    int64_t* d = (which ? sm.st_e : sm.st_s) + off + mis;      // window element k lives at d[k]
+    const int body = (ne - mis) > 0 ? ((ne - mis) & ~1) : 0;
+    mbar_arrive_expect_tx(&sm.bar, (uint32_t)body * 8u);
+    if (body > 0) bulk_g2s(d + mis, g + mis, (uint32_t)body * 8u, &sm.bar);
+    if (mis && ne > 0) d[0] = g[0];                              // unaligned head
+    if (ne - mis > body) d[ne - 1] = g[ne - 1];                  // odd tail
+    if (which) sm.woff_e[e] = off + mis;
+    else { sm.woff_s[e] = off + mis; sm.win_a[e] = a; sm.win_n[e] = ne; }
+  }
+  // ---- while the copies are in flight: tables, parameters, the own in-span
   if (tid < 64) sm.etab[tid] = c_exp2_64[tid];
   for (int r = tid; r <= kS3MaxR; r += kS3Threads) {
     sm.magic[r] = r >= 2 ? (uint32_t)(0xffffffffu / (uint32_t)r) + 1u : 0u;
@@ -299,25 +319,6 @@ k_score3(tw_batch b, tw_params prm, int has_params, int keep_windows, tw_score_o
   ws.ine[lane] = in_e;
 #pragma unroll
   for (int e = 0; e < E; ++e) { ws.used[lane][e][0] = 0u; ws.used[lane][e][1] = 0u; }
-  __syncthreads();                                   // mbarrier initialised
-
-  // ---- bulk copies: thread 2e stages the start times of ep e, thread 2e+1 the end times
-  if (tid < 2 * E) {
-    const int e = tid >> 1, which = tid & 1;
-    int off = 0;
-    for (int q = 0; q < e; ++q) off += (tw[2 * q + 1] + 3) & ~1;
-    const int a = tw[2 * e], ne = tw[2 * e + 1];
-    const int64_t* g = (which ? b.out_end : b.out_start) + b.ep_out_off[ep0 + e] + a;
-    const int mis = (int)((((uintptr_t)g) >> 3) & 1u);
-    int64_t* d = (which ? sm.st_e : sm.st_s) + off + mis;      // window element k lives at d[k]
-    const int body = (ne - mis) > 0 ? ((ne - mis) & ~1) : 0;
-    mbar_arrive_expect_tx(&sm.bar, (uint32_t)body * 8u);
-    if (body > 0) bulk_g2s(d + mis, g + mis, (uint32_t)body * 8u, &sm.bar);
-    if (mis && ne > 0) d[0] = g[0];                              // unaligned head
-    if (ne - mis > body) d[ne - 1] = g[ne - 1];                  // odd tail
-    if (which) sm.woff_e[e] = off + mis;
-    else { sm.woff_s[e] = off + mis; sm.win_a[e] = a; sm.win_n[e] = ne; }
-  }
   mbar_wait(&sm.bar, 0);
   __syncthreads();                                   // heads / tails / layout visible
 

@@ -160,8 +160,9 @@ def alibaba_stream(n_services: int = 2000, n_in: int = 1250, compress=(1, 200, 1
             factor = max(1, int(np.ceil(cf / replicas)))
             # an uncompressed service sees ~1 request per second; load 100 = one per 10 ms.  The generator
             # stops at load 50: with millisecond clocks the three-callee parallel shape at load 100 has
-            # 30-in-span windows of interchangeable candidates whose exact MWIS search exceeds the node
-            # budget of the engine (2 M per window, TW_ERR_MWIS_LIMIT) and of the oracle (20 M) alike
+            # 30-in-span windows of interchangeable candidates; the engine's search (priced bound,
+            # tw_core.cuh) finishes them in ~2e5 nodes, but the ORACLE's plain branch and bound — the
+            # checker of every bench leg — exceeds its 20 M-node budget there
             load = min(1.0 * factor, ALIBABA_MAX_LOAD)
             blocks.append(make_block(shape, per, n_in, load, seed + k, quantum_us=quantum_us))
             k += 1
