@@ -782,6 +782,7 @@ TW_HD uint32_t window_adjacency(const WindowBuf& wb, int E, int nw, int k) {
 // for interchangeable spans.  Same optimum as the MWIS formulation of V3:1252-1274.
 #define TW_ASSIGN_MAX_COLS (TW_WINDOW_CAP * (TW_K + 1) + 1)
 constexpr int kMwisPricedMin = 7;   // components of at least this many in-spans get the priced bound
+constexpr int kMwisSimpleBudget = 4096;   // nodes the plain search may spend on a component before the priced one takes over
 // `pos`: tuple position whose spans are the columns (E = 1: position 0 is the whole problem; E > 1: the
 // projection of the window on one callee, a RELAXATION whose dual prices bound the branch and bound
 // below).  best != nullptr: the matching (first tied optimum); price != nullptr: the dual price of
@@ -979,6 +980,76 @@ TW_HD_NOINLINE inline long long mwis_solve(WindowBuf& wb, int E, int nw, long lo
       for (int l = 0; l < m; ++l) wb.chosen[member[l]] = bst[l];
       nodes += m;
       continue;
+    }
+    // Two searches with the same answer (the first tied optimum in depth-first order): a plain one with
+    // the static bound "sum of the remaining in-spans' best weights" — a few instructions per node,
+    // enough for almost every window — and, when that one runs out of its small node budget, the
+    // search with availability masks and dual prices below (tens of times fewer nodes on windows
+    // whose in-spans compete for interchangeable spans, several times the work per node).
+    bool simple_done = true;
+    const long long nodes_at_start = nodes;
+    {
+      double ub[TW_WINDOW_CAP + 1];
+      ub[m] = 0.0;
+      for (int l = m - 1; l >= 0; --l) {
+        int k = member[l];
+        double mx = 0.0;
+        for (int r = 0; r < wb.cnt[k]; ++r) {
+          double w = TW_WEIGHT_OFFSET + wb.score[k][r];
+          if (w > mx) mx = w;
+        }
+        ub[l] = ub[l + 1] + mx;
+      }
+      int choice[TW_WINDOW_CAP], best[TW_WINDOW_CAP], iter[TW_WINDOW_CAP + 1];
+      double cur[TW_WINDOW_CAP + 1];
+      double best_w = -1.0;
+      for (int l = 0; l < m; ++l) best[l] = -1;
+      int level = 0;
+      cur[0] = 0.0;
+      iter[0] = 0;
+      while (level >= 0) {
+        if (level == m) {
+          ++nodes;
+          if (cur[m] > best_w + TW_MWIS_TIE_TOL) {   // a tied total never replaces an earlier leaf
+            best_w = cur[m];
+            for (int l = 0; l < m; ++l) best[l] = choice[l];
+          }
+          --level;
+          continue;
+        }
+        int k = member[level];
+        if (iter[level] == 0) {
+          ++nodes;
+          if (nodes - nodes_at_start > kMwisSimpleBudget) { simple_done = false; break; }
+          if (cur[level] + ub[level] <= best_w + TW_MWIS_TIE_TOL) { --level; continue; }
+        }
+        int r = iter[level]++;
+        if (r > wb.cnt[k]) { --level; continue; }
+        if (r == wb.cnt[k]) {  // leave in-span k unassigned
+          choice[level] = -1;
+          cur[level + 1] = cur[level];
+          ++level;
+          iter[level] = 0;
+          continue;
+        }
+        double w = TW_WEIGHT_OFFSET + wb.score[k][r];
+        if (!(w > 0.0)) continue;
+        bool ok = true;
+        for (int l = 0; l < level && ok; ++l)
+          if (choice[l] >= 0 && (wb.adj[k] >> member[l] & 1u) &&
+              tuples_conflict(wb.idx[k][r], wb.idx[member[l]][choice[l]], E))
+            ok = false;
+        if (!ok) continue;
+        choice[level] = r;
+        cur[level + 1] = cur[level] + w;
+        ++level;
+        iter[level] = 0;
+      }
+
+      if (simple_done) {
+        for (int l = 0; l < m; ++l) wb.chosen[member[l]] = best[l];
+        continue;
+      }
     }
     // Depth-first branch and bound over the component's in-spans in window order ("rank r", ranks
     // ascending, then "unassigned").  avail[L][j] = ranks of in-span j (j >= L) that are still

@@ -66,7 +66,7 @@ extern "C" int tw_debug_score_phases(unsigned long long* out24, int reset) {
 #endif
 
 #ifndef TW_S3_TBL
-#define TW_S3_TBL 320          // term-table slots per warp per round
+#define TW_S3_TBL 416          // term-table slots per warp per round
 #define TW_S3_ENT 192          // feasible tuples per warp between two flushes of the list
 #define TW_S3_PRM_TERMS 16     // likelihood records staged in shared memory (else read in place)
 #endif

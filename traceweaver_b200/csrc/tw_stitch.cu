@@ -34,6 +34,10 @@ __device__ unsigned long long g_stitch_phase[16];
 #define TW_SCOUNT(k, v) do { } while (0)
 #endif
 
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 struct StitchWarpSmem {
   ProbView v;
   WindowBuf wb;
@@ -235,7 +239,31 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
   bool skip_run = false;
   const bool can_run = tk_smem && spec.used_lo != nullptr && out.topk_score == nullptr;
   TW_SPHASE(0);                                  // setup + defaults
+  // The per-in-span records the run / adopt paths read (maps, top-K lists, counts) were written by the
+  // scoring kernel and are cold; every step of this sequential walk would otherwise wait for them one
+  // dependent miss after the other.  Each lane asks for the records of in-span (ws + 32 + lane) — one
+  // warp-width ahead of the step that will read them.
+  auto prefetch_ahead = [&](int first) {
+    const int ip = first + lane;
+    if (spec.used_lo == nullptr || ip >= n) return;
+    const int64_t gi = v.in_off + ip;
+    const int64_t base = v.tuple_off + (int64_t)ip * E;
+    prefetch_l1(spec.used_lo + base);
+    prefetch_l1(spec.used_bits + 2 * base);
+    prefetch_l1(spec.topk_idx + TW_K * base);
+    prefetch_l1(spec.topk_idx + TW_K * base + TW_K * E - 1);
+    prefetch_l1(spec.topk_score + gi * TW_K);
+    if ((lane & 15) == 0) {
+      prefetch_l1(spec.topk_cnt + gi);
+      prefetch_l1(spec.used_wide + gi);
+      prefetch_l1(spec.n_feasible + gi);
+      prefetch_l1(cut + ip);
+    }
+  };
+  prefetch_ahead(0);
+  int prefetched_to = 32;
   while (ws < n) {
+    if (ws + 32 >= prefetched_to) { prefetch_ahead(prefetched_to); prefetched_to += 32; }
     // ---- run of consecutive ONE-in-span windows, one lane each.  Windows only interact through
     // the taken bits, so if (a) every in-span of the run passes the fast-path test against the bits
     // taken so far and (b) the candidate maps of the run are pairwise disjoint, processing them
