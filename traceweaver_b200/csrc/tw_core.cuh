@@ -340,6 +340,11 @@ TW_HD void topk_toward_leaf(const ProbView& v, TopK& tk, int pos) {
 // Replayed literally (min-heap of at most K + 1 entries in heapq's array layout), so that the
 // surviving entries AND their array order are the reference's also when entries compare equal.
 TW_HD void topk_offer(const ProbView& v, TopK& tk, double score, const int* c) {
+  // A full heap and a score strictly below the root's: heappush moves the new entry to the root
+  // (its score is below every entry's) and heappop takes it out again, the last entry returning to
+  // the place it left — the array is exactly what it was.  Nothing to do (the common case once K good
+  // tuples are in).
+  if (tk.n == TW_K && score < tk.score[tk.heap[0]]) return;
   const int slot = tk.heap[tk.n];
   tk.score[slot] = score;
   for (int e = 0; e < v.E; ++e) tk.idx[slot][e] = c[e];
