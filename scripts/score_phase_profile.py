@@ -32,3 +32,5 @@ for label, prm in (("gauss pass (windows + top-K)", None), ("mixture pass (top-K
     rounds = max(buf[12], 1)
     print(f"  per in-span: slots {buf[10]/n_in:.2f} (valid {buf[14]/n_in:.2f}) combos {buf[11]/n_in:.2f} feasible {buf[13]/n_in:.2f}; "
           f"rounds per warp-tile {rounds/ (n_in/32):.2f}; warp cycles per in-span {tot/n_in:.0f}")
+    print(f"  tiles flagged for the sequential kernel: staging overflow {buf[15]}, range/combination limits {buf[16]} warps, "
+          f"ties/NaN {buf[17]} warps; tiles {eng.tile_count()}")

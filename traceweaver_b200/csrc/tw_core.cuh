@@ -951,8 +951,14 @@ TW_HD_NOINLINE inline void assignment_solve(const WindowBuf& wb, const int* memb
 
 // Solves the window; wb.adj must be filled.  Returns the number of search nodes, or -1 when
 // node_limit is exceeded (TW_ERR_MWIS_LIMIT).
-TW_HD_NOINLINE inline long long mwis_solve(WindowBuf& wb, int E, int nw, long long node_limit) {
+// `deferred` (device callers): components whose plain search ran out of its budget are not searched
+// here but returned as in-span masks (up to TW_MWIS_MAX_DEFERRED; *n_deferred counts them) for the
+// caller's warp-wide priced search (tw_stitch.cu); nullptr: everything is solved here.
+#define TW_MWIS_MAX_DEFERRED 4
+TW_HD_NOINLINE inline long long mwis_solve(WindowBuf& wb, int E, int nw, long long node_limit,
+                                           uint32_t* deferred = nullptr, int* n_deferred = nullptr) {
   long long nodes = 0;
+  if (n_deferred) *n_deferred = 0;
   uint32_t todo = nw >= 32 ? 0xffffffffu : ((1u << nw) - 1u);
   for (int k = 0; k < nw; ++k) wb.chosen[k] = -1;
   while (todo) {
@@ -1056,6 +1062,15 @@ TW_HD_NOINLINE inline long long mwis_solve(WindowBuf& wb, int E, int nw, long lo
         continue;
       }
     }
+    // (a component that exhausts the plain budget has many in-spans; a window of <= 31 in-spans
+    // cannot hold more than TW_MWIS_MAX_DEFERRED of them, so the list cannot overflow)
+    if (deferred && *n_deferred < TW_MWIS_MAX_DEFERRED) {
+      deferred[(*n_deferred)++] = comp;
+      continue;
+    }
+#ifdef __CUDA_ARCH__
+    return -1;   // device callers always pass `deferred`: the sequential priced search is host-only
+#else
     // Depth-first branch and bound over the component's in-spans in window order ("rank r", ranks
     // ascending, then "unassigned").  avail[L][j] = ranks of in-span j (j >= L) that are still
     // compatible with the choices made at levels < L; the bound of a node is the sum over the
@@ -1189,6 +1204,7 @@ TW_HD_NOINLINE inline long long mwis_solve(WindowBuf& wb, int E, int nw, long lo
       iter[level] = 0;
     }
     for (int l = 0; l < m; ++l) wb.chosen[member[l]] = best[l];
+#endif
   }
   return nodes;
 }

@@ -252,6 +252,7 @@ k_score3(tw_batch b, tw_params prm, int has_params, int keep_windows, tw_score_o
   for (int e = 0; e < E; ++e) tot += (tw[2 * e + 1] + 3) & ~1;
   if (tot > S3Smem<E>::kStage) {
     if (tid == 0 && !keep_windows) overflow_flag[t] = 1;
+    if (tid == 0) { TW_CCOUNT(15, 1); }           // staging overflow
     return;
   }
   if (tid == 0) mbar_init(&sm.bar, 2 * E);
@@ -355,6 +356,7 @@ k_score3(tw_batch b, tw_params prm, int has_params, int keep_windows, tw_score_o
   if (P > kS3MaxP) { anomaly = true; P = 0; }
   if (__any_sync(kFull, anomaly)) {
     if (lane == 0 && !keep_windows) overflow_flag[t] = 1;
+    TW_CCOUNT(16, 1);                                // range wider than 64 / too many combinations (per warp)
     return;   // (with keep_windows the flag is already set: same data, same decision)
   }
   // table size: root / sink-last terms r_e, edge terms r_b * r_e
@@ -713,6 +715,7 @@ k_score3(tw_batch b, tw_params prm, int has_params, int keep_windows, tw_score_o
   }
   if (__any_sync(kFull, redo)) {
     if (lane == 0) overflow_flag[t] = 1;       // (also under keep_windows: a score tie depends on the parameters)
+    TW_CCOUNT(17, 1);                                // tie / NaN (per warp)
     return;
   }
 

@@ -176,7 +176,158 @@ __device__ __forceinline__ bool stitch_small_window(StitchWarpSmem& sm, int E, i
   return true;
 }
 
-__global__ void __launch_bounds__(kStitchWarps * 32)
+
+// Priced branch and bound of ONE connected component by the whole warp (the sequential form is
+// mwis_solve's second search, tw_core.cuh: same order, same bounds, same tie rule).  Lane l owns the
+// l-th in-span of the component: its availability mask per level, its weights and prices.  A node is
+// expanded by all lanes at once — the owner's choice is broadcast, every later in-span strikes its
+// conflicting ranks, two warp sums give the bounds of the child — so a node costs tens of
+// instructions instead of the hundreds of the one-lane loop over (in-span, rank, tuple position).
+// `price` (shared scratch): dual prices of one callee's assignment relaxation, written by lane 0.
+__device__ __noinline__ long long mwis_component_warp(WindowBuf& wb, int E, uint32_t comp, double* price /*[31][TW_K]*/,
+                                                      long long node_limit, long long nodes, int lane) {
+  const unsigned kAll = 0xffffffffu;
+  // members in window order
+  const int m = __popc(comp);
+  int kmine = -1;                                   // own in-span (window index)
+  {
+    uint32_t c = comp;
+    for (int l = 0; l < m; ++l) {
+      const int k = __ffs(c) - 1;
+      c &= c - 1u;
+      if (l == lane) kmine = k;
+    }
+  }
+  // ---- prices: lane 0 solves the relaxation (callee with the fewest distinct spans)
+  double lam0 = 0.0;
+  if (lane == 0) {
+    int member[TW_WINDOW_CAP];
+    {
+      uint32_t c = comp;
+      for (int l = 0; l < m; ++l) { member[l] = __ffs(c) - 1; c &= c - 1u; }
+    }
+    int pos = 0, fewest = 0x7fffffff;
+    for (int e = 0; e < E; ++e) {
+      int distinct = 0;
+      for (int l = 0; l < m; ++l)
+        for (int r = 0; r < wb.cnt[member[l]]; ++r) {
+          const int sp = wb.idx[member[l]][r][e];
+          bool seen = false;
+          for (int l2 = 0; l2 <= l && !seen; ++l2)
+            for (int r2 = 0; r2 < (l2 < l ? wb.cnt[member[l2]] : r) && !seen; ++r2)
+              seen = wb.idx[member[l2]][r2][e] == sp;
+          distinct += !seen;
+        }
+      if (distinct < fewest) { fewest = distinct; pos = e; }
+    }
+    assignment_solve(wb, member, m, pos, nullptr, reinterpret_cast<double(*)[TW_K]>(price), &lam0);
+  }
+  __syncwarp();
+  lam0 = __shfl_sync(kAll, lam0, 0);
+  nodes += m;
+  const bool mine = lane < m;
+  const int cnt = mine ? wb.cnt[kmine] : 0;
+  double w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0, q4 = 0;   // weights, reduced weights
+  uint8_t av[TW_WINDOW_CAP + 1];
+  {
+    uint8_t mask = 0;
+    if (mine) {
+      double wv[TW_K], qv[TW_K];
+      for (int r = 0; r < TW_K; ++r) {
+        wv[r] = r < cnt ? TW_WEIGHT_OFFSET + wb.score[kmine][r] : 0.0;
+        qv[r] = wv[r] - price[lane * TW_K + r];
+        if (r < cnt && wv[r] > 0.0) mask |= (uint8_t)(1u << r);
+      }
+      w0 = wv[0]; w1 = wv[1]; w2 = wv[2]; w3 = wv[3]; w4 = wv[4];
+      q0 = qv[0]; q1 = qv[1]; q2 = qv[2]; q3 = qv[3]; q4 = qv[4];
+    }
+    av[0] = mask;
+  }
+  auto best_avail = [&](uint8_t mask) {           // lists are sorted: the lowest available rank is the heaviest
+    return (mask & 1u) ? w0 : (mask & 2u) ? w1 : (mask & 4u) ? w2 : (mask & 8u) ? w3 : (mask & 16u) ? w4 : 0.0;
+  };
+  auto best_reduced = [&](uint8_t mask) {
+    double mx = 0.0;
+    if ((mask & 1u) && q0 > mx) mx = q0;
+    if ((mask & 2u) && q1 > mx) mx = q1;
+    if ((mask & 4u) && q2 > mx) mx = q2;
+    if ((mask & 8u) && q3 > mx) mx = q3;
+    if ((mask & 16u) && q4 > mx) mx = q4;
+    return mx;
+  };
+  auto wsum = [&](double x) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(kAll, x, d);
+    return x;
+  };
+  double cur[TW_WINDOW_CAP + 1], rem[TW_WINDOW_CAP + 1], remp[TW_WINDOW_CAP + 1], lam[TW_WINDOW_CAP + 1];
+  int8_t iter[TW_WINDOW_CAP + 1];
+  rem[0] = wsum(best_avail(av[0]));
+  remp[0] = wsum(best_reduced(av[0]));
+  lam[0] = lam0;
+  cur[0] = 0.0;
+  iter[0] = 0;
+  int myc = -1, bestc = -1;
+  double best_w = -1.0;
+  int level = 0;
+  while (level >= 0) {
+    if (level == m) {
+      ++nodes;
+      if (cur[m] > best_w + TW_MWIS_TIE_TOL) { best_w = cur[m]; bestc = myc; }   // a tied total never replaces an earlier leaf
+      --level;
+      continue;
+    }
+    if (iter[level] == 0) {
+      ++nodes;
+      if (node_limit > 0 && nodes > node_limit) return -1;
+      double bound = rem[level] + 1e-7;
+      const double bp = remp[level] + lam[level] + 1e-7;
+      bound = bp < bound ? bp : bound;
+      if (cur[level] + bound <= best_w + TW_MWIS_TIE_TOL) { --level; continue; }
+    }
+    const int r = iter[level]++;
+    const int cntL = __shfl_sync(kAll, cnt, level);
+    if (r > cntL) { --level; continue; }
+    const uint8_t avmine = av[level];
+    const unsigned avL = __shfl_sync(kAll, (unsigned)avmine, level);
+    if (r == cntL) {                                // leave the in-span unassigned
+      const double ob = __shfl_sync(kAll, best_avail(avmine), level);
+      const double obp = __shfl_sync(kAll, best_reduced(avmine), level);
+      if (lane == level) myc = -1;
+      av[level + 1] = avmine;
+      cur[level + 1] = cur[level];
+      rem[level + 1] = rem[level] - ob;
+      remp[level + 1] = remp[level] - obp;
+      lam[level + 1] = lam[level];
+      ++level;
+      iter[level] = 0;
+      continue;
+    }
+    if (!(avL >> r & 1u)) continue;                 // weight <= 0, or struck by an earlier choice
+    const int kL = __shfl_sync(kAll, kmine, level);
+    uint8_t mask = avmine;
+    if (mine && lane > level && mask && (wb.adj[kL] >> kmine & 1u)) {
+      for (int q = 0; q < cnt; ++q)
+        if ((mask >> q & 1u) && tuples_conflict(wb.idx[kL][r], wb.idx[kmine][q], E)) mask &= (uint8_t)~(1u << q);
+    }
+    av[level + 1] = mask;
+    const bool later = mine && lane > level;
+    const double rest = wsum(later ? best_avail(mask) : 0.0);
+    const double restp = wsum(later ? best_reduced(mask) : 0.0);
+    if (lane == level) myc = r;
+    cur[level + 1] = cur[level] + (TW_WEIGHT_OFFSET + wb.score[kL][r]);
+    rem[level + 1] = rest;
+    remp[level + 1] = restp;
+    lam[level + 1] = lam[level] - price[level * TW_K + r];
+    ++level;
+    iter[level] = 0;
+  }
+  if (mine) wb.chosen[kmine] = bestc;
+  __syncwarp();
+  return nodes;
+}
+
+__global__ void __launch_bounds__(kStitchWarps * 32, 10)
 k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_score_out spec, tw_pass_out out,
          uint32_t* __restrict__ taken, long long node_limit, int* __restrict__ err_flag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -619,8 +770,18 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
         __syncwarp();
         if (lane < nw) wb.adj[lane] = window_adjacency(wb, E, nw, lane);
         __syncwarp();
-        if (lane == 0) nodes = mwis_solve(wb, E, nw, node_limit);
+        // lane 0: components one after the other (plain search, Hungarian for E = 1); components
+        // whose plain search runs out of budget come back and are searched by the whole warp
+        uint32_t deferred[TW_MWIS_MAX_DEFERRED];
+        int n_def = 0;
+        if (lane == 0) nodes = mwis_solve(wb, E, nw, node_limit, deferred, &n_def);
         nodes = __shfl_sync(0xffffffffu, nodes, 0);
+        n_def = __shfl_sync(0xffffffffu, n_def, 0);
+        for (int d = 0; d < n_def && nodes >= 0; ++d) {
+          const uint32_t comp = __shfl_sync(0xffffffffu, lane == 0 ? deferred[d] : 0u, 0);
+          __syncwarp();
+          nodes = mwis_component_warp(wb, E, comp, sm.tbl, node_limit, nodes, lane);
+        }
       }
     }
     __syncwarp();
