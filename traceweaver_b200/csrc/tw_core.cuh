@@ -787,7 +787,7 @@ TW_HD uint32_t window_adjacency(const WindowBuf& wb, int E, int nw, int k) {
 // for interchangeable spans.  Same optimum as the MWIS formulation of V3:1252-1274.
 #define TW_ASSIGN_MAX_COLS (TW_WINDOW_CAP * (TW_K + 1) + 1)
 constexpr int kMwisPricedMin = 7;   // components of at least this many in-spans get the priced bound
-constexpr int kMwisSimpleBudget = 4096;   // nodes the plain search may spend on a component before the priced one takes over
+constexpr int kMwisSimpleBudget = 1024;   // nodes the plain search may spend on a component before the priced one takes over
 // `pos`: tuple position whose spans are the columns (E = 1: position 0 is the whole problem; E > 1: the
 // projection of the window on one callee, a RELAXATION whose dual prices bound the branch and bound
 // below).  best != nullptr: the matching (first tied optimum); price != nullptr: the dual price of

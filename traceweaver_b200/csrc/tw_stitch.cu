@@ -327,6 +327,229 @@ __device__ __noinline__ long long mwis_component_warp(WindowBuf& wb, int E, uint
   return nodes;
 }
 
+// Search path of one window: the lanes flagged `todo` enumerate + score their in-span on the
+// not-yet-taken out spans (term tables in the warp's shared memory, evaluated by all lanes) and leave
+// their top-K lists in the window buffer.  Out of line on purpose: it is large and rarely taken (an
+// in-span gets here only when one of its candidates was taken by an earlier window).
+__device__ __noinline__ void stitch_search_lanes(StitchWarpSmem& sm, const tw_params& prm, const tw_pass_out& out,
+                                                 uint32_t* const* tk_base, const OutWin* w,
+                                                 const double* gauss_base, const double* mix_base, const double* etab,
+                                                 int E, int lane, int ws, int i, int64_t in_s, int64_t in_e,
+                                                 bool todo, int batch0) {
+  const ProbView& v = sm.v;
+  WindowBuf& wb = sm.wb;
+  auto is_taken = [&](int e, int o) {   // volatile: bits are set by other lanes with atomics
+    return (reinterpret_cast<volatile const uint32_t*>(tk_base[e])[o >> 5] >> (o & 31)) & 1u;
+  };
+  const bool active = todo, fast = false;
+  int lo[TW_MAX_E], r[TW_MAX_E], lo_abs[TW_MAX_E];
+  int tsize = 0;
+  if (active && !fast) {
+    for (int e = 0; e < E; ++e) {
+      lo[e] = lower_bound(w[e].s, w[e].n, in_s);
+      lo_abs[e] = lo[e];
+      r[e] = range_len(w[e], lo[e], in_e);
+    }
+    tsize = term_table_size(v, r);
+  }
+  const int brel = i / TW_PARAM_BATCH - batch0;
+  auto publish = [&](const TopK& tk, int leaves) {
+    const int64_t gi = v.in_off + i;
+    out.n_cand[gi] = leaves;
+    wb.cnt[lane] = tk.n;
+    for (int k = 0; k < tk.n; ++k) {
+      wb.score[lane][k] = tk.score[k];
+      for (int e = 0; e < E; ++e) wb.idx[lane][k][e] = tk.idx[k][e];
+    }
+    if (out.topk_score) {
+      out.topk_cnt[gi] = (uint8_t)tk.n;
+      int32_t* ix = out.topk_idx + TW_K * (v.tuple_off + (int64_t)i * E);
+      for (int k = 0; k < TW_K; ++k) {
+        out.topk_score[gi * TW_K + k] = k < tk.n ? tk.score[k] : __longlong_as_double(0x7ff8000000000000LL);
+        for (int e = 0; e < E; ++e) ix[k * E + e] = k < tk.n ? tk.idx[k][e] : -1;
+      }
+    }
+  };
+  bool pending = active;
+  // ---- heavy in-spans (thousands of candidate combinations), one at a time by the WHOLE warp:
+  // the owner lays out its term tables, all lanes evaluate the slots, then the lanes take the
+  // combinations lane, lane + 32, ... (ascending combination index = depth-first leaf order), keep
+  // their own top K and the warp merges the heads.  If two of the six best scores are equal the
+  // reference's heap order decides (tw_core.cuh topk_offer) and the owner redoes the in-span alone.
+  {
+    const long long Pown = pending ? combo_count(v, r) : 0;
+    unsigned heavy = __ballot_sync(0xffffffffu, pending && tsize <= kWarpTblCap && Pown > kStitchCoopCombos &&
+                                                    Pown < (1LL << 31));
+    while (heavy) {
+      const int L = __ffs(heavy) - 1;
+      heavy &= heavy - 1u;
+      int lo_b[TW_MAX_E], r_b[TW_MAX_E], o_last_b[TW_MAX_E];
+      for (int e = 0; e < E; ++e) {
+        lo_b[e] = __shfl_sync(0xffffffffu, lo[e], L);
+        r_b[e] = __shfl_sync(0xffffffffu, r[e], L);
+      }
+      const int tsz = __shfl_sync(0xffffffffu, tsize, L);
+      const int brel_b = __shfl_sync(0xffffffffu, brel, L);
+      const long long P_b = __shfl_sync(0xffffffffu, Pown, L);
+      term_table_last_offsets(v, r_b, o_last_b);
+      if (lane == L) term_table_fill(v, in_s, in_e, w, lo, r, o_last_b, brel_b, is_taken, sm.tbl, sm.sid);
+      __syncwarp();
+      for (int sl = lane; sl < tsz; sl += 32) {
+        const uint8_t id = sm.sid[sl];
+        if (id != TW_SLOT_INVALID) {
+          ParamView pv;
+          pv.mode = prm.mode;
+          pv.gauss = gauss_base ? gauss_base + (int64_t)(batch0 + (id >> 6)) * v.n_terms * TW_GAUSS_REC : nullptr;
+          pv.mix = mix_base;
+          pv.etab = etab;
+          sm.tbl[sl] = term_logpdf(pv, id & 63, sm.tbl[sl]);
+        }
+      }
+      __syncwarp();
+      TopK part;
+      part.clear();
+      int leaves = 0;
+      bool tie = false;
+      enumerate_combos(v, w, lo_b, r_b, o_last_b, sm.sid, lane, 32, P_b,
+                       [&](const int* c, const int64_t* ce, long long) {
+                         ++leaves;
+                         const double sc = table_score(v, r_b, lo_b, sm.tbl, c, ce);
+                         for (int k = 0; k < part.n; ++k) tie = tie || part.score[k] == sc;
+                         tie = tie || sc != sc;
+                         topk_offer_sorted(v, part, sc, c);
+                       });
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) leaves += __shfl_xor_sync(0xffffffffu, leaves, d);
+      TopK tkc;
+      tkc.clear();
+      int head = 0;
+      double prev = 0.0;
+      for (int round = 0; round <= TW_K; ++round) {
+        const double hs = head < part.n ? part.score[head] : -INFINITY;
+        double mx = hs;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          const double o = __shfl_xor_sync(0xffffffffu, mx, d);
+          mx = o > mx ? o : mx;
+        }
+        if (!(mx > -INFINITY)) break;
+        const unsigned who = __ballot_sync(0xffffffffu, hs == mx);
+        if (__popc(who) > 1 || (round > 0 && mx == prev)) tie = true;
+        prev = mx;
+        const int wl = __ffs(who) - 1;
+        if (round < TW_K) {
+          for (int e = 0; e < E; ++e) {
+            const int ci = __shfl_sync(0xffffffffu, head < part.n ? part.idx[head][e] : -1, wl);
+            if (lane == L) tkc.idx[round][e] = ci;
+          }
+          if (lane == L) { tkc.score[round] = mx; tkc.n = round + 1; }
+        }
+        if (lane == wl) ++head;
+      }
+      tie = __any_sync(0xffffffffu, tie);
+      if (!tie && lane == L) {
+        publish(tkc, leaves);
+        pending = false;
+      }
+      __syncwarp();
+    }
+  }
+  if (__any_sync(0xffffffffu, pending))
+  while (true) {
+    int my = pending ? tsize : 0, incl = my;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    const int offset = incl - my;
+    const bool lazy = pending && offset == 0 && tsize > kWarpTblCap;
+    const bool in_round = pending && !lazy && offset + tsize <= kWarpTblCap;
+    int total = in_round ? offset + tsize : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) total = max(total, __shfl_xor_sync(0xffffffffu, total, d));
+    int o_last[TW_MAX_E];
+    if (in_round) {
+      term_table_last_offsets(v, r, o_last);
+      term_table_fill(v, in_s, in_e, w, lo, r, o_last, brel, is_taken, sm.tbl + offset, sm.sid + offset);
+    }
+    if (lazy) {   // tables larger than the warp's slab: evaluate per leaf
+      ParamView pv;
+      pv.mode = prm.mode;
+      pv.gauss = gauss_base ? gauss_base + (int64_t)(i / TW_PARAM_BATCH) * v.n_terms * TW_GAUSS_REC : nullptr;
+      pv.mix = mix_base;
+      pv.etab = etab;
+      TopK tk;
+      tk.clear();
+      int leaves = 0;
+      enumerate(v, in_s, in_e, w, lo, is_taken,
+                [&](const int* c, const int64_t* cs, const int64_t* ce) {
+                  if (leaves < 0x7fffffff) ++leaves;
+                  topk_offer(v, tk, score_tuple(v, pv, in_s, in_e, cs, ce), c);
+                });
+      topk_finish(v, tk);
+      publish(tk, leaves);
+      pending = false;
+    }
+    __syncwarp();
+    for (int s = lane; s < total; s += 32) {     // GetEpPairCost for every slot, all lanes busy
+      const uint8_t id = sm.sid[s];
+      if (id != TW_SLOT_INVALID) {
+        ParamView pv;
+        pv.mode = prm.mode;
+        pv.gauss = gauss_base ? gauss_base + (int64_t)(batch0 + (id >> 6)) * v.n_terms * TW_GAUSS_REC : nullptr;
+        pv.mix = mix_base;
+        pv.etab = etab;
+        sm.tbl[s] = term_logpdf(pv, id & 63, sm.tbl[s]);
+      }
+    }
+    __syncwarp();
+    if (in_round) {
+      const double* tbl = sm.tbl + offset;
+      const uint8_t* sid = sm.sid + offset;
+      TopK tk;
+      tk.clear();
+      int leaves = 0;
+      enumerate(v, in_s, in_e, w, lo,
+                [&](int e, int o) { return sid[o_last[e] + (o - lo_abs[e])] == TW_SLOT_INVALID; },
+                [&](const int* c, const int64_t*, const int64_t* ce) {
+                  if (leaves < 0x7fffffff) ++leaves;
+                  topk_offer(v, tk, table_score(v, r, lo_abs, tbl, c, ce), c);
+                });
+      topk_finish(v, tk);
+      publish(tk, leaves);
+      pending = false;
+    }
+    if (!__any_sync(0xffffffffu, pending)) break;
+    __syncwarp();
+  }
+  __syncwarp();
+
+}
+
+// Exact MWIS of a window the small-window solver does not take (more than kSmallWindow in-spans, or
+// a component with too many leaves).  Out of line like the search path: large and comparatively rare.
+__device__ __noinline__ long long stitch_mwis_large(StitchWarpSmem& sm, int E, int nw, long long node_limit, int lane) {
+  WindowBuf& wb = sm.wb;
+  long long nodes = 1;
+  __syncwarp();
+  if (lane < nw) wb.adj[lane] = window_adjacency(wb, E, nw, lane);
+  __syncwarp();
+  // lane 0: components one after the other (plain search, Hungarian for E = 1); components
+  // whose plain search runs out of budget come back and are searched by the whole warp
+  uint32_t deferred[TW_MWIS_MAX_DEFERRED];
+  int n_def = 0;
+  if (lane == 0) nodes = mwis_solve(wb, E, nw, node_limit, deferred, &n_def);
+  nodes = __shfl_sync(0xffffffffu, nodes, 0);
+  n_def = __shfl_sync(0xffffffffu, n_def, 0);
+  for (int d = 0; d < n_def && nodes >= 0; ++d) {
+    const uint32_t comp = __shfl_sync(0xffffffffu, lane == 0 ? deferred[d] : 0u, 0);
+    __syncwarp();
+    nodes = mwis_component_warp(wb, E, comp, sm.tbl, node_limit, nodes, lane);
+  }
+  return nodes;
+}
+
 __global__ void __launch_bounds__(kStitchWarps * 32, 10)
 k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_score_out spec, tw_pass_out out,
          uint32_t* __restrict__ taken, long long node_limit, int* __restrict__ err_flag) {
@@ -549,35 +772,7 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
       }
       fast = hit == 0u;
     }
-    int lo[TW_MAX_E], r[TW_MAX_E], lo_abs[TW_MAX_E];
-    int tsize = 0;
-    if (active && !fast) {
-      for (int e = 0; e < E; ++e) {
-        lo[e] = lower_bound(w[e].s, w[e].n, in_s);
-        lo_abs[e] = lo[e];
-        r[e] = range_len(w[e], lo[e], in_e);
-      }
-      tsize = term_table_size(v, r);
-    }
     const int batch0 = ws / TW_PARAM_BATCH;
-    const int brel = i / TW_PARAM_BATCH - batch0;
-    auto publish = [&](const TopK& tk, int leaves) {
-      const int64_t gi = v.in_off + i;
-      out.n_cand[gi] = leaves;
-      wb.cnt[lane] = tk.n;
-      for (int k = 0; k < tk.n; ++k) {
-        wb.score[lane][k] = tk.score[k];
-        for (int e = 0; e < E; ++e) wb.idx[lane][k][e] = tk.idx[k][e];
-      }
-      if (out.topk_score) {
-        out.topk_cnt[gi] = (uint8_t)tk.n;
-        int32_t* ix = out.topk_idx + TW_K * (v.tuple_off + (int64_t)i * E);
-        for (int k = 0; k < TW_K; ++k) {
-          out.topk_score[gi * TW_K + k] = k < tk.n ? tk.score[k] : __longlong_as_double(0x7ff8000000000000LL);
-          for (int e = 0; e < E; ++e) ix[k * E + e] = k < tk.n ? tk.idx[k][e] : -1;
-        }
-      }
-    };
     if (fast) {   // adopt the list computed on the undeleted spans
       const int64_t gi = v.in_off + i;
       const int cnt = spec.topk_cnt[gi];
@@ -598,166 +793,12 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
       }
     }
     TW_SPHASE(5);                                // fast test + adopt
-    // ---- slow path: term tables of the window in the warp's shared memory, evaluated by all lanes
-    bool pending = active && !fast;
-#ifdef TW_PROFILE_PHASES
-    const int _n_slow = __popc(__ballot_sync(0xffffffffu, pending));
-    TW_SCOUNT(14, _n_slow);
-#endif
-    // ---- heavy in-spans (thousands of candidate combinations), one at a time by the WHOLE warp:
-    // the owner lays out its term tables, all lanes evaluate the slots, then the lanes take the
-    // combinations lane, lane + 32, ... (ascending combination index = depth-first leaf order), keep
-    // their own top K and the warp merges the heads.  If two of the six best scores are equal the
-    // reference's heap order decides (tw_core.cuh topk_offer) and the owner redoes the in-span alone.
-    {
-      const long long Pown = pending ? combo_count(v, r) : 0;
-      unsigned heavy = __ballot_sync(0xffffffffu, pending && tsize <= kWarpTblCap && Pown > kStitchCoopCombos &&
-                                                      Pown < (1LL << 31));
-      while (heavy) {
-        const int L = __ffs(heavy) - 1;
-        heavy &= heavy - 1u;
-        int lo_b[TW_MAX_E], r_b[TW_MAX_E], o_last_b[TW_MAX_E];
-        for (int e = 0; e < E; ++e) {
-          lo_b[e] = __shfl_sync(0xffffffffu, lo[e], L);
-          r_b[e] = __shfl_sync(0xffffffffu, r[e], L);
-        }
-        const int tsz = __shfl_sync(0xffffffffu, tsize, L);
-        const int brel_b = __shfl_sync(0xffffffffu, brel, L);
-        const long long P_b = __shfl_sync(0xffffffffu, Pown, L);
-        term_table_last_offsets(v, r_b, o_last_b);
-        if (lane == L) term_table_fill(v, in_s, in_e, w, lo, r, o_last_b, brel_b, is_taken, sm.tbl, sm.sid);
-        __syncwarp();
-        for (int sl = lane; sl < tsz; sl += 32) {
-          const uint8_t id = sm.sid[sl];
-          if (id != TW_SLOT_INVALID) {
-            ParamView pv;
-            pv.mode = prm.mode;
-            pv.gauss = gauss_base ? gauss_base + (int64_t)(batch0 + (id >> 6)) * v.n_terms * TW_GAUSS_REC : nullptr;
-            pv.mix = mix_base;
-            pv.etab = etab;
-            sm.tbl[sl] = term_logpdf(pv, id & 63, sm.tbl[sl]);
-          }
-        }
-        __syncwarp();
-        TopK part;
-        part.clear();
-        int leaves = 0;
-        bool tie = false;
-        enumerate_combos(v, w, lo_b, r_b, o_last_b, sm.sid, lane, 32, P_b,
-                         [&](const int* c, const int64_t* ce, long long) {
-                           ++leaves;
-                           const double sc = table_score(v, r_b, lo_b, sm.tbl, c, ce);
-                           for (int k = 0; k < part.n; ++k) tie = tie || part.score[k] == sc;
-                           tie = tie || sc != sc;
-                           topk_offer_sorted(v, part, sc, c);
-                         });
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) leaves += __shfl_xor_sync(0xffffffffu, leaves, d);
-        TopK tkc;
-        tkc.clear();
-        int head = 0;
-        double prev = 0.0;
-        for (int round = 0; round <= TW_K; ++round) {
-          const double hs = head < part.n ? part.score[head] : -INFINITY;
-          double mx = hs;
-#pragma unroll
-          for (int d = 16; d > 0; d >>= 1) {
-            const double o = __shfl_xor_sync(0xffffffffu, mx, d);
-            mx = o > mx ? o : mx;
-          }
-          if (!(mx > -INFINITY)) break;
-          const unsigned who = __ballot_sync(0xffffffffu, hs == mx);
-          if (__popc(who) > 1 || (round > 0 && mx == prev)) tie = true;
-          prev = mx;
-          const int wl = __ffs(who) - 1;
-          if (round < TW_K) {
-            for (int e = 0; e < E; ++e) {
-              const int ci = __shfl_sync(0xffffffffu, head < part.n ? part.idx[head][e] : -1, wl);
-              if (lane == L) tkc.idx[round][e] = ci;
-            }
-            if (lane == L) { tkc.score[round] = mx; tkc.n = round + 1; }
-          }
-          if (lane == wl) ++head;
-        }
-        tie = __any_sync(0xffffffffu, tie);
-        if (!tie && lane == L) {
-          publish(tkc, leaves);
-          pending = false;
-        }
-        __syncwarp();
-      }
-    }
-    if (__any_sync(0xffffffffu, pending))
-    while (true) {
-      int my = pending ? tsize : 0, incl = my;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        int o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += o;
-      }
-      const int offset = incl - my;
-      const bool lazy = pending && offset == 0 && tsize > kWarpTblCap;
-      const bool in_round = pending && !lazy && offset + tsize <= kWarpTblCap;
-      int total = in_round ? offset + tsize : 0;
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) total = max(total, __shfl_xor_sync(0xffffffffu, total, d));
-      int o_last[TW_MAX_E];
-      if (in_round) {
-        term_table_last_offsets(v, r, o_last);
-        term_table_fill(v, in_s, in_e, w, lo, r, o_last, brel, is_taken, sm.tbl + offset, sm.sid + offset);
-      }
-      if (lazy) {   // tables larger than the warp's slab: evaluate per leaf
-        ParamView pv;
-        pv.mode = prm.mode;
-        pv.gauss = gauss_base ? gauss_base + (int64_t)(i / TW_PARAM_BATCH) * v.n_terms * TW_GAUSS_REC : nullptr;
-        pv.mix = mix_base;
-        pv.etab = etab;
-        TopK tk;
-        tk.clear();
-        int leaves = 0;
-        enumerate(v, in_s, in_e, w, lo, is_taken,
-                  [&](const int* c, const int64_t* cs, const int64_t* ce) {
-                    if (leaves < 0x7fffffff) ++leaves;
-                    topk_offer(v, tk, score_tuple(v, pv, in_s, in_e, cs, ce), c);
-                  });
-        topk_finish(v, tk);
-        publish(tk, leaves);
-        pending = false;
-      }
-      __syncwarp();
-      for (int s = lane; s < total; s += 32) {     // GetEpPairCost for every slot, all lanes busy
-        const uint8_t id = sm.sid[s];
-        if (id != TW_SLOT_INVALID) {
-          ParamView pv;
-          pv.mode = prm.mode;
-          pv.gauss = gauss_base ? gauss_base + (int64_t)(batch0 + (id >> 6)) * v.n_terms * TW_GAUSS_REC : nullptr;
-          pv.mix = mix_base;
-          pv.etab = etab;
-          sm.tbl[s] = term_logpdf(pv, id & 63, sm.tbl[s]);
-        }
-      }
-      __syncwarp();
-      if (in_round) {
-        const double* tbl = sm.tbl + offset;
-        const uint8_t* sid = sm.sid + offset;
-        TopK tk;
-        tk.clear();
-        int leaves = 0;
-        enumerate(v, in_s, in_e, w, lo,
-                  [&](int e, int o) { return sid[o_last[e] + (o - lo_abs[e])] == TW_SLOT_INVALID; },
-                  [&](const int* c, const int64_t*, const int64_t* ce) {
-                    if (leaves < 0x7fffffff) ++leaves;
-                    topk_offer(v, tk, table_score(v, r, lo_abs, tbl, c, ce), c);
-                  });
-        topk_finish(v, tk);
-        publish(tk, leaves);
-        pending = false;
-      }
-      if (!__any_sync(0xffffffffu, pending)) break;
-      __syncwarp();
-    }
+    // ---- slow path (kept out of line: the hot loop above and below stays small in the instruction cache)
+    TW_SCOUNT(14, __popc(__ballot_sync(0xffffffffu, active && !fast)));
+    if (__any_sync(0xffffffffu, active && !fast))
+      stitch_search_lanes(sm, prm, out, tk_base, w, gauss_base, mix_base, etab, E, lane, ws, i, in_s, in_e,
+                          active && !fast, batch0);
     __syncwarp();
-
     TW_SPHASE(6);                                // slow path
     // ---- stitch the window (V3:1192-1219)
     long long nodes = 1;
@@ -767,21 +808,7 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
       bool solved = false;
       if (nw <= kSmallWindow) solved = stitch_small_window(sm, E, nw, lane, &nodes);
       if (!solved) {
-        __syncwarp();
-        if (lane < nw) wb.adj[lane] = window_adjacency(wb, E, nw, lane);
-        __syncwarp();
-        // lane 0: components one after the other (plain search, Hungarian for E = 1); components
-        // whose plain search runs out of budget come back and are searched by the whole warp
-        uint32_t deferred[TW_MWIS_MAX_DEFERRED];
-        int n_def = 0;
-        if (lane == 0) nodes = mwis_solve(wb, E, nw, node_limit, deferred, &n_def);
-        nodes = __shfl_sync(0xffffffffu, nodes, 0);
-        n_def = __shfl_sync(0xffffffffu, n_def, 0);
-        for (int d = 0; d < n_def && nodes >= 0; ++d) {
-          const uint32_t comp = __shfl_sync(0xffffffffu, lane == 0 ? deferred[d] : 0u, 0);
-          __syncwarp();
-          nodes = mwis_component_warp(wb, E, comp, sm.tbl, node_limit, nodes, lane);
-        }
+        nodes = stitch_mwis_large(sm, E, nw, node_limit, lane);
       }
     }
     __syncwarp();
