@@ -107,7 +107,7 @@ class Recorder:
         cls = v3mod.TraceWeaverV3
         self.orig = {n: getattr(cls, n) for n in (
             "FindAssignments", "FindTopKAssignments", "GetAssignmentsMIS", "CreateWindows2",
-            "ComputeEpPairDistParams3", "ComputeEpPairDistParams5")}
+            "ComputeEpPairDistParams3", "ComputeEpPairDistParams5", "TallySkipSpans", "BuildDistributions")}
         rec = self
 
         def FindAssignments(self_, method, process, in_parts, out_parts, parallel, hops, truth, graph, *a, **k):
@@ -136,6 +136,17 @@ class Recorder:
         def ComputeEpPairDistParams5(self_, in_parts, out_parts, graph, all_assignments, truth):
             res = rec.orig["ComputeEpPairDistParams5"](self_, in_parts, out_parts, graph, all_assignments, truth)
             rec.on_params5(self_)
+            return res
+
+        def TallySkipSpans(self_, in_parts, out_parts, in_eps, out_eps, batch_size_mis):
+            res = rec.orig["TallySkipSpans"](self_, in_parts, out_parts, in_eps, out_eps, batch_size_mis)
+            rec.on_tally(self_, out_eps)
+            return res
+
+        def BuildDistributions(self_, process, in_parts, out_parts, in_eps, out_eps):
+            res = rec.orig["BuildDistributions"](self_, process, in_parts, out_parts, in_eps, out_eps)
+            rec.cur["build_dist"] = rec._snap(self_.services_times)
+            rec.cur["large_delay"] = int(self_.large_delay)
             return res
 
         for n, f in list(locals().items()):
@@ -170,6 +181,11 @@ class Recorder:
             "iteration_marks": [],
         }
         cur["id2idx"] = {ep: {sid: i for i, sid in enumerate(ids)} for ep, ids in cur["out_ids"].items()}
+        # instance state the reference carries from one service to the next (V3:35-48 never resets it)
+        cur["time_windows_before"] = [tuple(w) for w in inst.time_windows]
+        cur["dist_values_before"] = {"|".join(k): list(map(float, v)) for k, v in inst.distribution_values.items()}
+        cur["dynamism_before"] = bool(inst.dynamism)
+        cur["skip_code"] = {}
         np.random.seed(GLOBAL_SEED)
         t0 = time.time()
         res = self.orig["FindAssignments"](inst, method, process, in_parts, out_parts, parallel, hops, truth, graph, *a, **k)
@@ -179,13 +195,15 @@ class Recorder:
         self.records.append(cur)
         self.cur = None
         if self.dump_as:          # write the fixture as soon as the service is done
-            print("minted", _dump(self.dump_as, cur, HERE), "%.0fs" % cur["seconds"], file=sys.__stdout__, flush=True)
+            print("minted", _dump(self.dump_as, cur, getattr(self, "dump_dir", HERE)), "%.0fs" % cur["seconds"], file=sys.__stdout__, flush=True)
         return res
 
     def _tuple_idx(self, out_eps, spans):
         idx = []
         for ep, s in zip(out_eps, spans[1:]):
-            assert s.trace_id != "None", "skip spans are outside the no-skip goldens"
+            if s.trace_id == "None":          # a skip span (V3:983-995): -2 - (its index among the ep's skip spans)
+                idx.append(-2 - self.cur["skip_code"][(ep, s.sid)])
+                continue
             idx.append(self.cur["id2idx"][ep][s.GetId()])
         return idx
 
@@ -201,6 +219,26 @@ class Recorder:
             return
         entry = [(float(score), self._tuple_idx(out_eps, spans)) for score, spans in res]
         (cur["topk"] if count else cur["topk2"]).append(entry)
+
+    def on_tally(self, inst, out_eps):
+        """After TallySkipSpans (V3:853-989): the time windows in FetchSkipFromWindow's order, the
+        water-filled skip counts, and an index for every skip span (windows in sorted order, then
+        position in the window's list) so that tuples can name them."""
+        cur = self.cur
+        wins = sorted(inst.time_windows, key=lambda x: x[0])
+        cur["time_windows"] = [tuple(w) for w in wins]
+        cur["skip_budget"] = {ep: int(inst.overall_skip_budget[ep]) for ep in out_eps}
+        cur["skip_count"] = {}
+        for ep in out_eps:
+            counts, g = [], 0
+            for w in wins:
+                lst = inst.available_skips_per_window[ep][tuple(w[:2])]
+                counts.append(len(lst))
+                for pos, (sp, used) in enumerate(lst):
+                    assert used == 0
+                    cur["skip_code"].setdefault((ep, sp.sid), g + pos)
+                g += len(lst)
+            cur["skip_count"][ep] = counts
 
     def on_mis(self, top_assignments, res):
         chosen = []
@@ -284,7 +322,7 @@ def _dump(dataset, rec, outdir):
             lst = all_topk[ep][iid]
             topk_final_cnt[i] = len(lst)
             for r, v in enumerate(lst):
-                topk_final[i, r, e] = id2idx[ep][v]
+                topk_final[i, r, e] = -2 if v == ("Skip", "Skip") else id2idx[ep][v]
 
     # MWIS choice: one chosen rank (or -1) per in-span and pass, in window order
     mis = np.full((passes, n), -9, np.int32)
@@ -339,6 +377,13 @@ def _dump(dataset, rec, outdir):
         "not_best_count": int(not_best), "num_spans": int(n_spans), "cnt_unassigned": int(cnt_un),
         "params_pass0": p3, "params_pass1": p5,
         "reference_seconds": rec["seconds"], "global_seed": GLOBAL_SEED,
+        # skip / cache mode (row f-4): state carried into the call, TallySkipSpans' and BuildDistributions' results
+        "time_windows_before": rec.get("time_windows_before", []), "time_windows": rec.get("time_windows", []),
+        "dynamism_before": rec.get("dynamism_before", False),
+        "dist_values_before_keys": sorted(rec.get("dist_values_before", {}).keys()),
+        "skip_budget": rec.get("skip_budget", {}), "skip_count": rec.get("skip_count", {}),
+        "large_delay": rec.get("large_delay"),
+        "build_dist": {"|".join(k): [v[1], v[2]] for k, v in rec.get("build_dist", {}).items() if v[0] == "gauss"},
         "versions": _versions(),
     }
     arrays = {
@@ -370,6 +415,14 @@ def _versions():
 
 
 def run_dataset(name, outdir, v3mod, recorder):
+    # "hotel_load150@0.2": the dataset with --cache_rate 0.2 (exps/exp2/run_experiment.sh); fixtures go
+    # to tests/golden_cache/ under the name hotel_load150_cache20
+    cache_rate = "0"
+    if "@" in name:
+        name, cache_rate = name.split("@")
+        outdir = os.path.join(os.path.dirname(HERE), "golden_cache")
+        os.makedirs(outdir, exist_ok=True)
+    label = name if cache_rate == "0" else f"{name}_cache{int(round(float(cache_rate) * 100))}"
     rel, fix = DATASETS[name]
     scratch = tempfile.mkdtemp(prefix="tw_golden_")
     data = os.path.join(scratch, name)
@@ -379,7 +432,7 @@ def run_dataset(name, outdir, v3mod, recorder):
         os.remove(cache)
     results = os.path.join(scratch, "results") + "/"
     os.makedirs(results)
-    argv = ["executor.py", "--absolute_path", data, "--compressed", "0", "--cache_rate", "0",
+    argv = ["executor.py", "--absolute_path", data, "--compressed", "0", "--cache_rate", cache_rate,
             "--fix", str(fix), "--test_name", name, "--load_level", "0", "--compress_factor", "1",
             "--repeat_factor", "1", "--execute_parallel", "0", "--results_directory", results,
             "--clear_cache", "0", "--predictor_indices", "10"]
@@ -388,7 +441,8 @@ def run_dataset(name, outdir, v3mod, recorder):
     os.chdir(scratch)
     buf = io.StringIO()
     recorder.records = []
-    recorder.dump_as = name
+    recorder.dump_as = label
+    recorder.dump_dir = outdir
     t0 = time.time()
     try:
         sys.stdout = buf
@@ -400,13 +454,13 @@ def run_dataset(name, outdir, v3mod, recorder):
     wall = time.time() - t0
     log = buf.getvalue()
     acc_lines = [l for l in log.splitlines() if "ccuracy" in l and "iteration" not in l]
-    paths = [_dump(name, rec, outdir) for rec in recorder.records]
+    paths = [_dump(label, rec, outdir) for rec in recorder.records]
     if os.environ.get("TW_GOLDEN_ONLY") or os.environ.get("TW_GOLDEN_SKIP"):
         return paths, {"printed_accuracy": [], "wall_seconds": wall}      # partial run: no summary file
-    summary = {"dataset": name, "fix": fix, "wall_seconds": wall,
+    summary = {"dataset": label, "fix": fix, "cache_rate": float(cache_rate), "wall_seconds": wall,
                "find_assignments_seconds": {r["process"]: r["seconds"] for r in recorder.records},
                "printed_accuracy": acc_lines, "versions": _versions()}
-    with open(os.path.join(outdir, f"{name}.json"), "w") as f:
+    with open(os.path.join(outdir, f"{label}.json"), "w") as f:
         json.dump(summary, f, indent=1)
     shutil.rmtree(scratch, ignore_errors=True)
     return paths, summary
