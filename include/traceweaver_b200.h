@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TW_ABI_VERSION 2
+#define TW_ABI_VERSION 3
 
 /* Algorithm constants hard-coded by the reference. */
 #define TW_MAX_E 8             /* engine limit on out-eps per service (shipped data: <= 4)      */
@@ -56,8 +56,12 @@ typedef enum tw_status {
   TW_ERR_CUDA = -2,           /* a CUDA runtime call failed; see tw_last_error()                 */
   TW_ERR_MWIS_LIMIT = -3,     /* exact MWIS branch-and-bound exceeded its node budget            */
   TW_ERR_RANGE_LIMIT = -4,    /* an in-span has more candidates per ep than the engine supports  */
-  TW_ERR_UNSUPPORTED = -5,    /* skip budgets != 0 (n_out != n_in): SURVEY.md §8 row f-4, not built */
-  TW_ERR_NO_DEVICE = -6       /* no CUDA device / wrong architecture                              */
+  TW_ERR_UNSUPPORTED = -5,    /* skip budgets != 0 (n_out != n_in) handed to the two-pass entry points:
+                                 such services go through tw_skip_solve                            */
+  TW_ERR_NO_DEVICE = -6,      /* no CUDA device / wrong architecture                              */
+  TW_ERR_REFERENCE_UNDEFINED = -7 /* skip mode: the reference itself raises on this input (two tuples
+                                 with equal scores that differ in a skip span, an all-skip tuple, a
+                                 chain of skipped ancestors, a missing distribution key)          */
 } tw_status;
 
 /* Term kinds of the score (traceweaver_v1.py:316-357). */
@@ -248,6 +252,57 @@ int tw_gmm_refit(tw_engine* eng, const int64_t* term_sample_off, const double* d
  */
 int tw_gmm_stream_draws(tw_engine* eng, const int64_t* term_sample_off, const double* delays,
                         const int32_t* counts, uint32_t* prob_draws_out, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Skip / cache mode.  A service some of whose outgoing lists do not
+ * hold one span per incoming span (overall_skip_budget != 0, traceweaver_v3.py:1138-1158 — cache hits,
+ * exps/exp2) takes ONE iteration with skip spans: TallySkipSpans (v3:853-989), BuildDistributions
+ * (v3:108-172), FetchSkipFromWindow (v3:820-842), the skip branch of DfsTraverseX (v3:316-324) and
+ * skip-aware, normalised scoring (traceweaver_v1.py:133-136, :264-292).
+ *
+ * The batch is a tw_batch whose out lists are sorted by start (stable) as TallySkipSpans leaves them
+ * (v3:968-971); n_out may differ from n_in.  Because the reference builds its windows and its
+ * with-deletion search on the lists in the CALLER's order (which executor.py's cache transform leaves
+ * partly unsorted), that order travels as a permutation.  Result indices refer to the sorted lists;
+ * a skip span is the code -2 - g, g = its index among the ep's skip spans (time windows in start
+ * order, then position inside the window); tw_pass_out.assign holds -2 for ("Skip", "Skip").
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tw_skip_desc {
+  const int64_t* prob_win_off;    /* [P+1] time windows of problem p (self.time_windows, v3:973-985,
+                                     including the ones earlier services left in the instance)      */
+  const int64_t* win_start;       /* [prob_win_off[P]] window starts, sorted per problem (v3:830)    */
+  const int64_t* prob_cnt_off;    /* [P+1] offset into skip_count: E_p * n_win_p entries per problem */
+  const int32_t* skip_count;      /* skip_count[prob_cnt_off[p] + e*n_win_p + w]: skip spans WaterFill
+                                     gives ep e in window w (v3:863-917; host mirror, np.argsort ties) */
+  const int64_t* prob_pair_off;   /* [P+1] offset into pair_gauss in records: (E_p+1)^2 per problem  */
+  const double* pair_gauss;       /* [.][2] (mean, std) of services_times[(a, b)] after BuildDistributions,
+                                     a, b: 0 = incoming endpoint, 1 + e = out ep e; NaN mean = no key */
+  const uint8_t* prob_normalized; /* [P] 1 iff some budget > 0 (scores are means of densities, v3:222-227) */
+  const int8_t* ep_pred_order;    /* [n_ep_total][TW_MAX_E] predecessors of the ep in in_edges order, -1 padded */
+  const int32_t* out_entry_pos;   /* [n_out_total] position of sorted span j in the caller's list (ep-local) */
+  const int32_t* out_sorted_of_entry; /* [n_out_total] inverse permutation                            */
+} tw_skip_desc;
+
+typedef struct tw_skip_out {
+  tw_pass_out pass;       /* assign (-2 = Skip), mis_rank, n_cand, with-deletion top-K (may be NULL), counters */
+  double* top2_score;     /* [n_in_total][K] top_k_2 on the undeleted lists (v3:1185), NaN padded    */
+  int32_t* top2_idx;      /* layout of tw_pass_out.topk_idx                                          */
+  uint8_t* top2_cnt;      /* [n_in_total]                                                            */
+  uint8_t* cut;           /* [n_in_total] PerfectCut flags as the reference computes them (v3:1024-1039) */
+} tw_skip_out;
+
+/* One iteration of every problem of `dev` (DEVICE pointers; `host_desc`: HOST copies of the descriptor
+ * arrays as for tw_engine_bind).  Does not touch a batch bound with tw_engine_bind. */
+int tw_skip_solve(tw_engine* eng, const tw_batch* dev, const tw_batch* host_desc, const tw_skip_desc* dev_skip,
+                  const tw_skip_out* out, void* stream);
+
+/* The parent search of BuildDistributions (v3:120-168) over one service's spans merged by start
+ * (stable: incoming spans first, then the out eps in topological order).  label[i]: 0 = incoming
+ * (server) span, 1 + e = span of out ep e.  key_out[i] = parent_label * (E + 1) + label or -1,
+ * val_out[i] = the delay sample.  All pointers DEVICE. */
+int tw_build_dist_samples(tw_engine* eng, int32_t n, const int64_t* start, const int64_t* end, const int8_t* label,
+                          int32_t E, int64_t large_delay, int32_t* key_out, int64_t* val_out, void* stream);
 
 #ifdef __cplusplus
 }

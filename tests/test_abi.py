@@ -42,6 +42,8 @@ def test_struct_layout_matches_header(lib):
     assert C.sizeof(_abi.TwParams) == 8 + 3 * 8
     assert C.sizeof(_abi.TwPassOut) == 7 * 8
     assert C.sizeof(_abi.TwScoreOut) == 9 * 8
+    assert C.sizeof(_abi.TwSkipDesc) == 10 * 8
+    assert C.sizeof(_abi.TwSkipOut) == 7 * 8 + 4 * 8
 
 
 def test_host_validation(lib):
@@ -54,8 +56,8 @@ def test_host_validation(lib):
     p.out_end[1] = p.out_end[1][:-1]
     hb2 = build_batch([p])
     st2 = batch_struct(hb2, lambda n: hb2.arrays[n].ctypes.data)
-    assert lib.tw_batch_validate_host(C.byref(st2)) == -5
-    assert b"skip" in lib.tw_last_error()
+    assert lib.tw_batch_validate_host(C.byref(st2)) == -5      # the two-pass entry points; tw_skip_solve takes it
+    assert b"tw_skip_solve" in lib.tw_last_error()
 
 
 def test_no_device_fails_loudly(lib):

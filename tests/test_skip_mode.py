@@ -1,0 +1,164 @@
+"""Skip / cache mode.
+
+CPU: the literal oracle (oracle/tw_oracle_skip.py) and the host mirror's NumPy pieces
+(traceweaver_b200/skipmode.py) against fixtures minted from the reference run with --cache_rate
+(tests/golden_cache/, tests/golden/make_goldens.py <dataset>@<rate>).
+GPU: tw_skip_solve / tw_build_dist_samples through the C ABI against the same fixtures and the oracle."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from golden_util import Golden
+from oracle import tw_oracle_skip as osk
+from traceweaver_b200 import skipmode
+
+CACHE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_cache")
+
+
+def cache_files(skip_only=True):
+    out = []
+    for f in sorted(glob.glob(os.path.join(CACHE_DIR, "*__*.npz"))):
+        g = Golden(f)
+        has_skip = any(v != 0 for v in g.meta["skip_budget"].values())
+        if has_skip or not skip_only:
+            out.append(f)
+    return out
+
+
+FILES = cache_files()
+IDS = [os.path.basename(f)[:-4] for f in FILES]
+
+
+def _inputs(g):
+    prob = g.problem()          # lists in the caller's order (the cache transform leaves them partly unsorted)
+    wins_before = [tuple(w) for w in g.meta["time_windows_before"]]
+    return prob, wins_before
+
+
+def _check_against_golden(g, res, exact_scores):
+    z, m = g.z, g.meta
+    assert [tuple(w) for w in m["time_windows"]] == [tuple(w) for w in res["time_windows"]]
+    assert [m["skip_budget"][ep] for ep in g.topo] == list(res["skip_budget"])
+    assert np.array_equal(np.asarray([m["skip_count"][ep] for ep in g.topo]), np.asarray(res["skip_count"]))
+    labels = [m["in_ep"]] + g.topo
+    for k, (mu, sd) in m["build_dist"].items():
+        a, b = k.split("|")
+        if a in labels and b in labels:
+            got = res["pair_params"][labels.index(a), labels.index(b)]
+            assert got[0] == mu and got[1] == sd, k
+    assert res["large_delay"] == m["large_delay"]
+    assert np.array_equal(res["topk2_idx"], z["topk2_idx"][0])
+    assert np.array_equal(res["topk_idx"], z["topk_idx"][0])
+    assert np.array_equal(res["topk_cnt"], z["topk_cnt"][0])
+    if exact_scores:
+        assert np.array_equal(res["topk_score"], z["topk_score"][0], equal_nan=True)
+        assert np.array_equal(res["topk2_score"], z["topk2_score"][0], equal_nan=True)
+    else:   # device exp() vs NumPy's: 1e-5 is the contract (BASELINE.json), observed ~1e-19 absolute
+        assert np.allclose(res["topk_score"], z["topk_score"][0], rtol=1e-12, atol=0, equal_nan=True)
+        assert np.allclose(res["topk2_score"], z["topk2_score"][0], rtol=1e-12, atol=0, equal_nan=True)
+    assert np.array_equal(res["mis_rank"], z["mis_rank"][0])
+    assert np.array_equal(res["assign"], z["assign"])
+    assert np.array_equal(res["n_cand"], z["per_span_candidates"])
+    assert res["not_best_count"] == m["not_best_count"]
+    assert res["cnt_unassigned"] == m["cnt_unassigned"]
+
+
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_oracle_equals_reference(path):
+    g = Golden(path)
+    prob, wins_before = _inputs(g)
+    res = osk.solve_skip(prob.in_start, prob.in_end, prob.out_start, prob.out_end, prob.preds,
+                         time_windows_before=wins_before)
+    assert res["windows"] == [tuple(w) for w in g.meta["windows"]]
+    _check_against_golden(g, res, exact_scores=True)
+
+
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_host_mirror_tally_equals_reference(path):
+    """time windows + WaterFill of traceweaver_b200.skipmode (NumPy) against the reference's."""
+    g = Golden(path)
+    prob, wins_before = _inputs(g)
+    st = skipmode.SkipState()
+    st.time_windows = list(wins_before)
+    sorted_start = [np.sort(np.asarray(o, np.int64), kind="stable") for o in prob.out_start]
+    wins, budgets, counts = skipmode.tally(prob.in_start, prob.in_end, sorted_start, st)
+    assert [tuple(w) for w in g.meta["time_windows"]] == wins
+    assert [g.meta["skip_budget"][ep] for ep in g.topo] == budgets
+    assert np.array_equal(np.asarray([g.meta["skip_count"][ep] for ep in g.topo]), counts)
+
+
+def test_norm_pdf_restatement_matches_scipy():
+    import scipy.stats
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        x, loc, sc = rng.normal(0, 3000), rng.normal(500, 300), abs(rng.normal(800, 500)) + 1e-3
+        assert osk.norm_pdf(x, loc, sc) == float(scipy.stats.norm.pdf(x, loc=loc, scale=sc))
+        assert osk.norm_logpdf(x, loc, sc) == float(scipy.stats.norm.logpdf(x, loc=loc, scale=sc))
+
+
+def test_exact_mwis_prefers_true_optimum_below_float_noise():
+    # two in-spans, two ranks each; (rank 0, rank 0) and (rank 1, rank 1) are the independent pairs and
+    # their totals differ by 3e-10 in favour of the second (the size of the gap in hotel_load150_cache20,
+    # window 797-798): a tolerance of 1e-9 would call that a tie and return the first
+    a = [(0.00029014, (10, 20)), (0.00029010, (10, 21))]
+    b = [(0.00030727, (11, 21)), (0.00030731 + 3e-10, (11, 20))]
+    assert osk.exact_mwis([a, b]) == [1, 1]
+    b[1] = (0.00030731 - 3e-10, (11, 20))
+    assert osk.exact_mwis([a, b]) == [0, 0]
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_engine_equals_reference(path):
+    from traceweaver_b200.engine import Engine
+    g = Golden(path)
+    prob, wins_before = _inputs(g)
+    eng = Engine(0)
+    st = skipmode.SkipState()
+    st.time_windows = list(wins_before)
+    res = skipmode.solve(eng, prob.in_start, prob.in_end, prob.out_start, prob.out_end, prob.preds,
+                         labels=[g.meta["in_ep"]] + g.topo, state=st)
+    eng.close()
+    # PerfectCut flags -> the reference's window list
+    from oracle import tw_oracle
+    assert tw_oracle.windows_from_cuts(res["cut"]) == [tuple(w) for w in g.meta["windows"]]
+    res = dict(res, topk2_idx=res["top2_idx"], topk2_score=res["top2_score"],
+               not_best_count=int(res["counters"][0, 0]), cnt_unassigned=int(res["counters"][0, 1]))
+    _check_against_golden(g, res, exact_scores=False)
+
+
+@pytest.mark.gpu
+def test_engine_equals_oracle_on_synthetic_skips():
+    """A generated service with cache hits on TWO eps (skip spans at two tuple positions, which no shipped
+    dataset has): engine == oracle, index for index."""
+    from traceweaver_b200.engine import Engine
+    rng = np.random.default_rng(5)
+    n = 240
+    in_s = np.cumsum(rng.integers(2000, 9000, n)).astype(np.int64) + 1_600_000_000_000_000
+    dur = rng.integers(20000, 40000, n)
+    in_e = in_s + dur
+    o0s = in_s + rng.integers(200, 900, n)
+    o0e = o0s + rng.integers(3000, 6000, n)
+    o1s = o0e + rng.integers(200, 900, n)
+    o1e = o1s + rng.integers(3000, 6000, n)
+    keep0 = np.sort(rng.choice(n, n - 30, replace=False))
+    keep1 = np.sort(rng.choice(n, n - 17, replace=False))
+    outs_s = [np.sort(o0s[keep0]), o1s[keep1]]
+    outs_e = [o0e[keep0][np.argsort(o0s[keep0], kind="stable")], o1e[keep1]]
+    od = np.argsort(outs_s[1], kind="stable")
+    outs_s[1], outs_e[1] = outs_s[1][od], outs_e[1][od]
+    preds = [[], [0]]
+    ref = osk.solve_skip(in_s, in_e, outs_s, outs_e, preds)
+    eng = Engine(0)
+    res = skipmode.solve(eng, in_s, in_e, outs_s, outs_e, preds)
+    eng.close()
+    assert np.array_equal(res["skip_count"], np.asarray(ref["skip_count"]))
+    assert np.array_equal(res["top2_idx"], ref["topk2_idx"])
+    assert np.array_equal(res["topk_idx"], ref["topk_idx"])
+    assert np.array_equal(res["mis_rank"], ref["mis_rank"])
+    assert np.array_equal(res["assign"], ref["assign"])
+    assert np.allclose(res["topk_score"], ref["topk_score"], rtol=1e-12, atol=0, equal_nan=True)
+    assert (res["assign"] == -2).sum() > 0

@@ -4,7 +4,7 @@ Field order and widths must match the header exactly; tests/test_abi.py checks s
 against values compiled from the header."""
 import ctypes as C
 
-TW_ABI_VERSION = 2
+TW_ABI_VERSION = 3
 TW_SCORE_KEEP_WINDOWS = 1
 TW_MAX_E = 8
 TW_K = 5
@@ -22,10 +22,11 @@ TW_PARAMS_GAUSS_BATCHED = 0
 TW_PARAMS_MIXTURE = 1
 
 TW_OK = 0
-TW_ERR_INVALID, TW_ERR_CUDA, TW_ERR_MWIS_LIMIT, TW_ERR_RANGE_LIMIT, TW_ERR_UNSUPPORTED, TW_ERR_NO_DEVICE = \
-    -1, -2, -3, -4, -5, -6
+TW_ERR_INVALID, TW_ERR_CUDA, TW_ERR_MWIS_LIMIT, TW_ERR_RANGE_LIMIT, TW_ERR_UNSUPPORTED, TW_ERR_NO_DEVICE, \
+    TW_ERR_REFERENCE_UNDEFINED = -1, -2, -3, -4, -5, -6, -7
 STATUS = {0: "TW_OK", -1: "TW_ERR_INVALID", -2: "TW_ERR_CUDA", -3: "TW_ERR_MWIS_LIMIT",
-          -4: "TW_ERR_RANGE_LIMIT", -5: "TW_ERR_UNSUPPORTED", -6: "TW_ERR_NO_DEVICE"}
+          -4: "TW_ERR_RANGE_LIMIT", -5: "TW_ERR_UNSUPPORTED", -6: "TW_ERR_NO_DEVICE",
+          -7: "TW_ERR_REFERENCE_UNDEFINED"}
 
 P = C.c_void_p
 
@@ -54,6 +55,16 @@ class TwScoreOut(C.Structure):
     _fields_ = [("topk_score", P), ("topk_idx", P), ("topk_cnt", P), ("n_feasible", P), ("cut", P),
                 ("used_lo", P), ("used_bits", P), ("used_wide", P), ("flags", C.c_uint32),
                 ("reserved0", C.c_uint32)]
+
+
+class TwSkipDesc(C.Structure):
+    _fields_ = [("prob_win_off", P), ("win_start", P), ("prob_cnt_off", P), ("skip_count", P),
+                ("prob_pair_off", P), ("pair_gauss", P), ("prob_normalized", P), ("ep_pred_order", P),
+                ("out_entry_pos", P), ("out_sorted_of_entry", P)]
+
+
+class TwSkipOut(C.Structure):
+    _fields_ = [("pass_", TwPassOut), ("top2_score", P), ("top2_idx", P), ("top2_cnt", P), ("cut", P)]
 
 
 class TwError(RuntimeError):

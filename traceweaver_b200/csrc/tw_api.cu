@@ -55,6 +55,11 @@ struct tw_engine {
   uint8_t* own_used_wide = nullptr;
   uint32_t* taken = nullptr;
   size_t taken_words = 0;
+  // skip / cache mode scratch (tw_skip_solve)
+  uint32_t* skip_sets = nullptr;
+  int64_t* skip_set_off = nullptr;
+  uint32_t* skip_taken = nullptr;
+  int32_t* skip_win = nullptr;
   int* err_flag = nullptr;
   int64_t* in_end_sorted = nullptr;
   int64_t* out_end_sorted = nullptr;
@@ -144,7 +149,10 @@ int tw_engine_destroy(tw_engine* eng) {
   return TW_OK;
 }
 
-int tw_batch_validate_host(const tw_batch* h) {
+static int validate_host(const tw_batch* h, bool allow_skip);
+int tw_batch_validate_host(const tw_batch* h) { return validate_host(h, false); }
+
+static int validate_host(const tw_batch* h, bool allow_skip) {
   if (!h || h->n_problems < 1) return fail(TW_ERR_INVALID, "batch: no problems");
   if (!h->prob_in_off || !h->prob_ep_off || !h->prob_tuple_off || !h->ep_out_off || !h->ep_term_off ||
       !h->ep_pred_mask || !h->term_src)
@@ -165,7 +173,9 @@ int tw_batch_validate_host(const tw_batch* h) {
     if (nt < E || nt > TW_MAX_TERMS) return fail(TW_ERR_INVALID, "batch: term count out of range");
     for (int e = 0; e < E; ++e) {
       int64_t no = h->ep_out_off[ep0 + e + 1] - h->ep_out_off[ep0 + e];
-      if (no != n) return fail(TW_ERR_UNSUPPORTED, "batch: n_out != n_in (skip budgets, SURVEY §8 f-4) unsupported");
+      if (no != n && !allow_skip)
+        return fail(TW_ERR_UNSUPPORTED, "batch: n_out != n_in (skip budgets): use tw_skip_solve for this service");
+      if (no < 1) return fail(TW_ERR_INVALID, "batch: an outgoing list is empty");
       uint32_t pm = h->ep_pred_mask[ep0 + e];
       if (pm >> e) return fail(TW_ERR_INVALID, "batch: predecessor mask must reference earlier eps only");
       int t0 = h->ep_term_off[ep0 + e], t1 = h->ep_term_off[ep0 + e + 1];
@@ -300,7 +310,8 @@ int tw_engine_status(tw_engine* eng, void* stream_) {
   if (flag != 0) {
     CU(cudaMemsetAsync(eng->err_flag, 0, sizeof(int), s));
     return fail(flag, "device-side status %s", flag == TW_ERR_MWIS_LIMIT ? "TW_ERR_MWIS_LIMIT"
-                                               : flag == TW_ERR_RANGE_LIMIT ? "TW_ERR_RANGE_LIMIT" : "error");
+                                               : flag == TW_ERR_RANGE_LIMIT ? "TW_ERR_RANGE_LIMIT"
+                                               : flag == TW_ERR_REFERENCE_UNDEFINED ? "TW_ERR_REFERENCE_UNDEFINED" : "error");
   }
   return TW_OK;
 }
@@ -321,6 +332,61 @@ int tw_engine_tile_stats(tw_engine* eng, int64_t* n_tiles, int64_t* n_redone, vo
       for (uint8_t f : h) *n_redone += f != 0;
     }
   }
+  return TW_OK;
+}
+
+int tw_skip_solve(tw_engine* eng, const tw_batch* dev, const tw_batch* h, const tw_skip_desc* sd, const tw_skip_out* out,
+                  void* stream_) {
+  if (!eng || !dev || !h || !sd || !out) return fail(TW_ERR_INVALID, "tw_skip_solve: NULL argument");
+  int rc = validate_host(h, true);
+  if (rc) return rc;
+  if (!out->pass.assign || !out->pass.mis_rank || !out->pass.n_cand || !out->pass.counters || !out->top2_score ||
+      !out->top2_idx || !out->top2_cnt || !out->cut)
+    return fail(TW_ERR_INVALID, "tw_skip_solve: NULL output array");
+  if ((out->pass.topk_score != nullptr) != (out->pass.topk_idx != nullptr) ||
+      (out->pass.topk_score != nullptr) != (out->pass.topk_cnt != nullptr))
+    return fail(TW_ERR_INVALID, "tw_skip_solve: topk_* must be all set or all NULL");
+  cudaStream_t s = (cudaStream_t)stream_;
+  CU(cudaSetDevice(eng->device));
+  const int P = h->n_problems;
+  // candidate-set bitmaps: three per problem, one word-aligned stretch per ep
+  std::vector<int64_t> set_off((size_t)P + 1, 0);
+  for (int p = 0; p < P; ++p) {
+    int64_t words = 0;
+    for (int ep = h->prob_ep_off[p]; ep < h->prob_ep_off[p + 1]; ++ep)
+      words += (h->ep_out_off[ep + 1] - h->ep_out_off[ep] + 31) / 32;
+    set_off[p + 1] = set_off[p] + words;
+  }
+  CU(eng->alloc(&eng->skip_sets, (size_t)(3 * set_off[P])));
+  CU(eng->alloc(&eng->skip_set_off, (size_t)P + 1));
+  CU(eng->alloc(&eng->skip_taken, (size_t)(h->n_out_total / 32) + (size_t)h->n_ep_total + 2));
+  // per (ep, window) prefix + fetch counters: the host does not know prob_cnt_off (device array), so
+  // size it by an upper bound the caller's skip_count array must respect: read the last offset
+  int64_t cnt_total = 0;
+  CU(cudaMemcpyAsync(&cnt_total, sd->prob_cnt_off + P, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (cnt_total < 0) return fail(TW_ERR_INVALID, "tw_skip_solve: prob_cnt_off inconsistent");
+  CU(eng->alloc(&eng->skip_win, (size_t)(2 * cnt_total)));
+  {
+    int* before = eng->err_flag;
+    CU(eng->alloc(&eng->err_flag, 1));
+    if (eng->err_flag != before) CU(cudaMemsetAsync(eng->err_flag, 0, sizeof(int), s));
+  }
+  CU(cudaMemcpyAsync(eng->skip_set_off, set_off.data(), set_off.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  CU(launch_skip(*dev, *sd, *out, eng->skip_taken, eng->skip_sets, eng->skip_set_off, eng->skip_win, eng->node_limit,
+                 eng->err_flag, s));
+  CU(cudaStreamSynchronize(s));    // set_off goes out of scope
+  eng->launches += 1;
+  return TW_OK;
+}
+
+int tw_build_dist_samples(tw_engine* eng, int32_t n, const int64_t* start, const int64_t* end, const int8_t* label,
+                          int32_t E, int64_t large_delay, int32_t* key_out, int64_t* val_out, void* stream_) {
+  if (!eng || n < 0 || !start || !end || !label || !key_out || !val_out || E < 1 || E > TW_MAX_E)
+    return fail(TW_ERR_INVALID, "tw_build_dist_samples: bad argument");
+  CU(cudaSetDevice(eng->device));
+  CU(launch_build_dist(n, start, end, label, E, large_delay, key_out, val_out, (cudaStream_t)stream_));
+  eng->launches += 1;
   return TW_OK;
 }
 

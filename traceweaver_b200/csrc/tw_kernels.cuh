@@ -87,4 +87,10 @@ cudaError_t launch_gmm_fit(int n_terms, const int64_t* term_sample_off, const do
                            const double* stream100, double* bic, double* cen, double* mix_out,
                            int32_t* n_selected_out, int* err_flag, GmmFork* fk, cudaStream_t s);
 
+cudaError_t launch_skip(const tw_batch& b, const tw_skip_desc& sd, const tw_skip_out& out, uint32_t* taken,
+                        uint32_t* set_scratch, const int64_t* prob_set_off, int32_t* win_scratch,
+                        long long node_limit, int* err_flag, cudaStream_t s);
+cudaError_t launch_build_dist(int n, const int64_t* ms, const int64_t* me, const int8_t* label, int E,
+                              int64_t large_delay, int32_t* key, int64_t* val, cudaStream_t s);
+
 }  // namespace tw
