@@ -395,3 +395,29 @@ extern "C" int twe_small_window(int nw, int E, const int* cnt_in, const double* 
   }
   return 1;
 }
+
+// ---------------------------------------------------------------------------------------------
+// skip / cache mode (tw_skip_core.cuh): the kernel body of k_skip and k_build_dist on the CPU
+// ---------------------------------------------------------------------------------------------
+#include "../../traceweaver_b200/csrc/tw_skip_core.cuh"
+
+extern "C" int twe_skip_solve(const tw_batch* b, const tw_skip_desc* sd, const tw_skip_out* out, long long node_limit) {
+  const int P = b->n_problems;
+  std::vector<int64_t> set_off((size_t)P + 1, 0);
+  for (int p = 0; p < P; ++p) {
+    int64_t words = 0;
+    for (int ep = b->prob_ep_off[p]; ep < b->prob_ep_off[p + 1]; ++ep)
+      words += (b->ep_out_off[ep + 1] - b->ep_out_off[ep] + 31) / 32;
+    set_off[p + 1] = set_off[p] + words;
+  }
+  std::vector<uint32_t> sets((size_t)(3 * set_off[P]) + 1), taken((size_t)(b->n_out_total / 32) + (size_t)b->n_ep_total + 2);
+  std::vector<int32_t> win((size_t)(2 * sd->prob_cnt_off[P]) + 1);
+  int rc = TW_OK;
+  SkipShared* sh = new SkipShared;
+  for (int p = 0; p < P; ++p) {
+    const int r = skip_solve_problem(*b, p, *sd, *out, taken.data(), sets.data(), set_off.data(), win.data(), node_limit, *sh);
+    if (r < rc) rc = r;
+  }
+  delete sh;
+  return rc;
+}

@@ -78,3 +78,30 @@ class EmulBatch(OracleBatch):
             _check(lib().twe_stitch_problem(C.byref(self.struct), p, C.byref(prm), _ptr(cut), C.byref(out),
                                             C.c_longlong(self.node_limit)), "emul.stitch")
         return res
+
+
+def skip_solve(in_start, in_end, out_start, out_end, preds, wins, counts, pair, budgets, node_limit=4000000):
+    """k_skip's body (tw_skip_core.cuh) stepped on the CPU, fed through the product's own marshalling
+    (traceweaver_b200.skipmode.marshal) with host pointers.  Results in the caller's list order."""
+    from traceweaver_b200 import skipmode
+    from traceweaver_b200.batch import batch_struct
+    in_start = np.ascontiguousarray(in_start, np.int64)
+    in_end = np.ascontiguousarray(in_end, np.int64)
+    order, s_start, s_end = skipmode.sort_partitions(out_start, out_end)
+    hb, host = skipmode.marshal(in_start, in_end, s_start, s_end, order, preds, wins, counts, pair, budgets)
+    E, n = len(out_start), len(in_start)
+    nt = n * E
+    out = dict(assign=np.full(nt, -9, np.int32), mis_rank=np.full(n, -9, np.int8), n_cand=np.zeros(n, np.int32),
+               topk_score=np.full((n, _abi.TW_K), np.nan), topk_idx=np.full(_abi.TW_K * nt, -1, np.int32),
+               topk_cnt=np.zeros(n, np.uint8), counters=np.zeros((1, 4), np.int32),
+               top2_score=np.full((n, _abi.TW_K), np.nan), top2_idx=np.full(_abi.TW_K * nt, -1, np.int32),
+               top2_cnt=np.zeros(n, np.uint8), cut=np.zeros(n, np.uint8))
+    sd = _abi.TwSkipDesc(*[_ptr(host[f]) for f, _ in _abi.TwSkipDesc._fields_])
+    so = _abi.TwSkipOut(_abi.TwPassOut(*[_ptr(out[k]) for k in ("assign", "mis_rank", "n_cand", "topk_score", "topk_idx",
+                                                                 "topk_cnt", "counters")]),
+                        _ptr(out["top2_score"]), _ptr(out["top2_idx"]), _ptr(out["top2_cnt"]), _ptr(out["cut"]))
+    st = batch_struct(hb, lambda name: _ptr(hb.arrays[name]))
+    L = lib()
+    L.twe_skip_solve.restype = C.c_int
+    _check(L.twe_skip_solve(C.byref(st), C.byref(sd), C.byref(so), C.c_longlong(node_limit)), "emul.skip_solve")
+    return skipmode.to_caller_order(out, order, n, E)

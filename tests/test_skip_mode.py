@@ -89,6 +89,26 @@ def test_host_mirror_tally_equals_reference(path):
     assert np.array_equal(np.asarray([g.meta["skip_count"][ep] for ep in g.topo]), counts)
 
 
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_device_code_stepped_on_cpu_equals_reference(path):
+    """The kernel body of k_skip (tw_skip_core.cuh, compiled for the CPU by tests/emul) on the fixtures;
+    time windows, skip counts and the BuildDistributions table come from the oracle here."""
+    import emul_backend
+    from oracle import tw_oracle
+    g = Golden(path)
+    prob, wins_before = _inputs(g)
+    ref = osk.solve_skip(prob.in_start, prob.in_end, prob.out_start, prob.out_end, prob.preds,
+                         time_windows_before=wins_before)
+    res = emul_backend.skip_solve(prob.in_start, prob.in_end, prob.out_start, prob.out_end, prob.preds,
+                                  ref["time_windows"], ref["skip_count"], ref["pair_params"], ref["skip_budget"])
+    assert tw_oracle.windows_from_cuts(res["cut"]) == [tuple(w) for w in g.meta["windows"]]
+    res = dict(res, topk2_idx=res["top2_idx"], topk2_score=res["top2_score"],
+               not_best_count=int(res["counters"][0, 0]), cnt_unassigned=int(res["counters"][0, 1]),
+               time_windows=ref["time_windows"], skip_budget=ref["skip_budget"], skip_count=ref["skip_count"],
+               pair_params=ref["pair_params"], large_delay=ref["large_delay"])
+    _check_against_golden(g, res, exact_scores=False)
+
+
 def test_norm_pdf_restatement_matches_scipy():
     import scipy.stats
     rng = np.random.default_rng(3)
@@ -162,3 +182,40 @@ def test_engine_equals_oracle_on_synthetic_skips():
     assert np.array_equal(res["assign"], ref["assign"])
     assert np.allclose(res["topk_score"], ref["topk_score"], rtol=1e-12, atol=0, equal_nan=True)
     assert (res["assign"] == -2).sum() > 0
+
+
+@pytest.mark.gpu
+def test_predictor_runs_a_cache_directory_like_the_reference():
+    """The drop-in `TraceWeaverV3.FindAssignments` on the services of one cache-mode run in the executor's
+    order (frontend with skip budgets first, then search without): ONE predictor instance carries the
+    time windows / distribution samples from service to service like the reference's; the 6-tuples equal
+    the reference's (assignments incl. ("Skip", "Skip"), top-K lists, counters, candidates per span)."""
+    from test_gpu_pipeline import reference_call_args
+    from traceweaver_b200.predictor import TraceWeaverV3
+    files = sorted(glob.glob(os.path.join(CACHE_DIR, "hotel_load150_cache20__*.npz")))
+    gs = {Golden(f).meta["process"]: Golden(f) for f in files}
+    pred = TraceWeaverV3({}, {}, device=0)
+    for process in ("frontend", "search"):
+        g = gs[process]
+        assert [tuple(w) for w in g.meta["time_windows_before"]] == [tuple(w) for w in pred.skip_state.time_windows]
+        in_parts, out_parts, truth, G = reference_call_args(g)
+        if process == "frontend":       # the fixture's truth holds -1 where the reference's dict says ('Skip', 'Skip')
+            for e, ep in enumerate(g.topo):
+                for i, j in enumerate(g.z["truth"][e]):
+                    if j < 0:
+                        truth[ep][(str(g.z["in_trace"][i]), str(g.z["in_sid"][i]))] = ("Skip", "Skip")
+        a, topk, not_best, n, cands, unassigned = pred.FindAssignments(
+            "MaxScoreBatchSubsetWithSkips", process, in_parts, out_parts, False, [], truth, G)
+        z, m = g.z, g.meta
+        assert (not_best, n, unassigned) == (m["not_best_count"], m["num_spans"], m["cnt_unassigned"])
+        in_ids = [s.GetId() for s in list(in_parts.values())[0]]
+        for e, ep in enumerate(g.topo):
+            ids = [s.GetId() for s in out_parts[ep]]
+            for i, iid in enumerate(in_ids):
+                c = int(z["assign"][e, i])
+                want = ids[c] if c >= 0 else (("NA", "NA") if c == -1 else ("Skip", "Skip"))
+                assert a[ep][iid] == want, (process, ep, i)
+                wl = [ids[c] if c >= 0 else ("Skip", "Skip") for c in z["topk_final"][i, :z["topk_final_cnt"][i], e]]
+                assert topk[ep][iid] == wl, (process, ep, i)
+        for i, iid in enumerate(in_ids):
+            assert cands.get(iid, 0) == int(z["per_span_candidates"][i])

@@ -11,12 +11,13 @@ INTEGRATION.md).  All compute is in the CUDA engine behind the C ABI; this file 
 import numpy as np
 import torch
 
-from . import _abi, refit
+from . import _abi, refit, skipmode
 from .batch import Problem, build_batch
 from .engine import Engine
 
 METHOD = "MaxScoreBatchSubsetWithSkips"
 NA = ("NA", "NA")
+SKIP = ("Skip", "Skip")
 
 
 def solve_batch(eng: Engine, hb, seed_select=10, truth_assign=None, term_order=None, device_arrays=None,
@@ -64,12 +65,16 @@ def solve_bound(eng: Engine, seed_select=10, truth_assign=None, term_order=None,
 class TraceWeaverV3:
     """`predictors` entry replacing the reference's ("MaxScoreBatchSubsetWithSkips", TraceWeaverV3)."""
 
-    def __init__(self, all_spans, all_processes, device=0, seed_select=10):
+    def __init__(self, all_spans, all_processes, device=0, seed_select=10, carry_state=True):
         self.all_spans = all_spans
         self.all_processes = all_processes
         self.seed_select = seed_select
         self.engine = Engine(device)          # raises without a CUDA device: there is no CPU path
         self.last = None
+        # what the reference's instance keeps from one service to the next and its skip regime reads
+        # (time_windows, distribution_values: traceweaver_v3.py:40,45 are never reset)
+        self.skip_state = skipmode.SkipState()
+        self.carry_state = carry_state
 
     # -- marshalling -------------------------------------------------------------------------------
     @staticmethod
@@ -103,12 +108,11 @@ class TraceWeaverV3:
         in_ep, in_spans = list(in_span_partitions.items())[0]
         # TallySkipSpans re-sorts every partition by start (stable), traceweaver_v3.py:968-971
         in_spans = sorted(in_spans, key=lambda x: float(x.start_mus))
+        if any(len(p) != len(in_spans) for p in out_span_partitions.values()):
+            # skip budgets (cache hits / dynamism): ONE iteration with skip spans, traceweaver_v3.py:1138-1158
+            return self._find_assignments_skip(process, in_ep, in_spans, out_span_partitions, true_assignments,
+                                               invocation_graph)
         out_parts = {ep: sorted(p, key=lambda x: float(x.start_mus)) for ep, p in out_span_partitions.items()}
-        for ep, p in out_parts.items():
-            if len(p) != len(in_spans):
-                raise NotImplementedError(
-                    f"endpoint {ep!r}: {len(p)} outgoing vs {len(in_spans)} incoming spans — skip budgets "
-                    "(cache hits / dynamism, SURVEY.md §8 row f-4) are not built; use the reference for them")
         prob, out_eps = self._problem(process, in_spans, out_parts, invocation_graph)
         hb = build_batch([prob])
         n, E = prob.n_in, prob.E
@@ -124,6 +128,14 @@ class TraceWeaverV3:
         given_pos = [out_eps.index(ep) for ep in out_span_partitions.keys()]
         order = np.asarray(refit.reference_term_order(prob, given_pos), np.int32)
 
+        if self.carry_state:
+            # the reference runs TallySkipSpans and BuildDistributions for EVERY service (v3:1136, :1149);
+            # in this regime they only leave state behind for a later service with skip budgets
+            labels = [in_ep] + out_eps
+            st = self.skip_state
+            st.time_windows.extend(skipmode.new_time_windows(prob.in_start, prob.in_end))
+            skipmode.build_distributions(self.engine, prob.in_start, prob.in_end, prob.out_start, prob.out_end,
+                                         labels, st)
         dev = self.engine.device
         res = solve_batch(self.engine, hb, seed_select=self.seed_select,
                           truth_assign=torch.from_numpy(truth.reshape(-1)).to(dev),
@@ -149,3 +161,39 @@ class TraceWeaverV3:
             if n_cand[i] or in_ids[i] in per_span_candidates:
                 per_span_candidates[in_ids[i]] = int(n_cand[i])
         return (all_assignments, all_topk, int(counters[0, 0]), n, per_span_candidates, int(counters[0, 1]))
+
+    # -- skip / cache mode --------------------------------------------------
+    def _find_assignments_skip(self, process, in_ep, in_spans, out_span_partitions, true_assignments,
+                               invocation_graph):
+        import networkx as nx
+        out_eps = list(nx.topological_sort(invocation_graph))            # traceweaver_v1.py:37-39
+        if set(out_eps) != set(out_span_partitions.keys()):
+            raise ValueError("invocation_graph nodes must be the outgoing endpoints")
+        pos = {ep: i for i, ep in enumerate(out_eps)}
+        in_s, in_e = self._arrays(in_spans)
+        outs = [self._arrays(out_span_partitions[ep]) for ep in out_eps]     # the caller's list order
+        preds = [[pos[b] for b, _ in invocation_graph.in_edges(ep)] for ep in out_eps]
+        state = self.skip_state if self.carry_state else skipmode.SkipState()
+        res = skipmode.solve(self.engine, in_s, in_e, [o[0] for o in outs], [o[1] for o in outs], preds,
+                             labels=[in_ep] + out_eps, state=state, want_topk=False)
+        self.last = res
+        n, E = len(in_spans), len(out_eps)
+        in_ids = [s.GetId() for s in in_spans]
+        out_ids = [[s.GetId() for s in out_span_partitions[ep]] for ep in out_eps]
+
+        def name(e, c):
+            return out_ids[e][c] if c >= 0 else (NA if c == -1 else SKIP)    # traceweaver_v1.py:446-453
+        assign, top2, cnt = res["assign"], res["top2_idx"], res["top2_cnt"]
+        all_assignments = {ep: {in_ids[i]: name(e, int(assign[e, i])) for i in range(n)} for e, ep in enumerate(out_eps)}
+        all_topk = {ep: {in_ids[i]: [name(e, int(top2[i, r, e])) for r in range(cnt[i])] for i in range(n)}
+                    for e, ep in enumerate(out_eps)}
+        per_span_candidates = {}
+        for ep in out_span_partitions.keys():                            # traceweaver_v3.py:1096-1098
+            for key in (true_assignments.get(ep, {}) if true_assignments else {}):
+                per_span_candidates[key] = 0
+        n_cand = res["n_cand"]
+        for i in range(n):
+            if n_cand[i] or in_ids[i] in per_span_candidates:
+                per_span_candidates[in_ids[i]] = int(n_cand[i])
+        ctr = res["counters"]
+        return (all_assignments, all_topk, int(ctr[0, 0]), n, per_span_candidates, int(ctr[0, 1]))

@@ -130,6 +130,52 @@ def build_distributions(engine, in_start, in_end, sorted_out_start, sorted_out_e
     return tab, large_delay
 
 
+def sort_partitions(out_start, out_end):
+    """TallySkipSpans sorts every partition by float(start), stable (V3:968-971).  Returns the
+    permutations (sorted j -> caller's position) and the sorted arrays."""
+    order = [np.argsort(np.asarray(o, np.int64).astype(np.float64), kind="stable") for o in out_start]
+    s_start = [np.ascontiguousarray(np.asarray(o, np.int64)[od]) for o, od in zip(out_start, order)]
+    s_end = [np.ascontiguousarray(np.asarray(o, np.int64)[od]) for o, od in zip(out_end, order)]
+    return order, s_start, s_end
+
+
+def marshal(in_start, in_end, s_start, s_end, order, preds, wins, counts, pair, budgets):
+    """Host arrays of tw_batch + tw_skip_desc for ONE service (sorted lists + the caller's order)."""
+    E = len(s_start)
+    prob = Problem(in_start=in_start, in_end=in_end, out_start=s_start, out_end=s_end, preds=preds, name="skip")
+    hb = build_batch([prob])
+    n_win = len(wins)
+    pred_order = np.full((E, _abi.TW_MAX_E), -1, np.int8)
+    for e, pl in enumerate(preds):
+        pred_order[e, :len(pl)] = pl
+    entry_pos = np.concatenate(order).astype(np.int32)                       # sorted j -> caller's position
+    sorted_of_entry = np.concatenate([np.argsort(od) for od in order]).astype(np.int32)
+    host = dict(prob_win_off=np.array([0, n_win], np.int64), win_start=np.array([w[0] for w in wins], np.int64),
+                prob_cnt_off=np.array([0, E * n_win], np.int64),
+                skip_count=np.ascontiguousarray(np.asarray(counts).reshape(-1), np.int32),
+                prob_pair_off=np.array([0, (E + 1) ** 2], np.int64),
+                pair_gauss=np.ascontiguousarray(np.asarray(pair, np.float64).reshape(-1)),
+                prob_normalized=np.array([1 if any(b > 0 for b in budgets) else 0], np.uint8),
+                ep_pred_order=pred_order.reshape(-1), out_entry_pos=entry_pos, out_sorted_of_entry=sorted_of_entry)
+    return hb, host
+
+
+def to_caller_order(res, order, n, E, want_topk=True):
+    """Result indices refer to the sorted lists: translate to positions in the caller's lists (codes < 0 stay)."""
+    def conv(idx, ep_last):
+        idx = idx.copy()
+        for e in range(E):
+            col = idx[..., e] if ep_last else idx[e]
+            m = col >= 0
+            col[m] = order[e][col[m]]
+        return idx
+    res["assign"] = conv(res["assign"].reshape(E, n), False)
+    res["top2_idx"] = conv(res["top2_idx"].reshape(n, _abi.TW_K, E), True)
+    if want_topk:
+        res["topk_idx"] = conv(res["topk_idx"].reshape(n, _abi.TW_K, E), True)
+    return res
+
+
 def solve(engine, in_start, in_end, out_start, out_end, preds, labels=None, state: SkipState = None,
           want_topk=True):
     """One FindAssignments call in the skip regime for ONE service.  out_start/out_end: per ep
@@ -141,31 +187,16 @@ def solve(engine, in_start, in_end, out_start, out_end, preds, labels=None, stat
     labels = labels or list(range(E + 1))
     in_start = np.ascontiguousarray(in_start, np.int64)
     in_end = np.ascontiguousarray(in_end, np.int64)
-    # TallySkipSpans sorts every partition by float(start), stable (V3:968-971)
-    order = [np.argsort(np.asarray(o, np.int64).astype(np.float64), kind="stable") for o in out_start]
-    s_start = [np.ascontiguousarray(np.asarray(o, np.int64)[od]) for o, od in zip(out_start, order)]
-    s_end = [np.ascontiguousarray(np.asarray(o, np.int64)[od]) for o, od in zip(out_end, order)]
+    order, s_start, s_end = sort_partitions(out_start, out_end)
     wins, budgets, counts = tally(in_start, in_end, s_start, state)
     pair, large_delay = build_distributions(engine, in_start, in_end, s_start, s_end, labels, state)
-
-    prob = Problem(in_start=in_start, in_end=in_end, out_start=s_start, out_end=s_end, preds=preds, name="skip")
-    hb = build_batch([prob])
+    hb, host = marshal(in_start, in_end, s_start, s_end, order, preds, wins, counts, pair, budgets)
     dev = engine.device
-    n, nt, n_win = prob.n_in, prob.n_in * E, len(wins)
+    n, nt = len(in_start), len(in_start) * E
 
     def up(a):
         return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
-    pred_order = np.full((E, _abi.TW_MAX_E), -1, np.int8)
-    for e, pl in enumerate(preds):
-        pred_order[e, :len(pl)] = pl
-    entry_pos = np.concatenate(order).astype(np.int32)                       # sorted j -> caller's position
-    sorted_of_entry = np.concatenate([np.argsort(od) for od in order]).astype(np.int32)
-    host = dict(prob_win_off=np.array([0, n_win], np.int64), win_start=np.array([w[0] for w in wins], np.int64),
-                prob_cnt_off=np.array([0, E * n_win], np.int64), skip_count=counts.reshape(-1).astype(np.int32),
-                prob_pair_off=np.array([0, (E + 1) ** 2], np.int64), pair_gauss=pair.reshape(-1),
-                prob_normalized=np.array([1 if any(b > 0 for b in budgets) else 0], np.uint8),
-                ep_pred_order=pred_order.reshape(-1), out_entry_pos=entry_pos, out_sorted_of_entry=sorted_of_entry)
     d = {k: up(v) for k, v in host.items()}
     db = {k: up(v.view(np.int32) if v.dtype == np.uint32 else v) for k, v in hb.arrays.items()}
     sd = _abi.TwSkipDesc(*[C.c_void_p(d[f].data_ptr()) for f, _ in _abi.TwSkipDesc._fields_])
@@ -189,20 +220,7 @@ def solve(engine, in_start, in_end, out_start, out_end, preds, labels=None, stat
     _lib.check(engine.lib.tw_skip_solve(engine.h, C.byref(dev_struct), C.byref(host_struct), C.byref(sd), C.byref(so),
                                         engine.stream), "tw_skip_solve")
     engine.status()
-    res = {k: v.cpu().numpy() for k, v in out.items()}
-
-    def to_entry(idx, e_axis_last=True):
-        """sorted-list indices -> positions in the caller's lists (codes < 0 stay)."""
-        idx = idx.copy()
-        for e in range(E):
-            col = idx[..., e] if e_axis_last else idx[e]
-            m = col >= 0
-            col[m] = order[e][col[m]]
-        return idx
-    res["assign"] = to_entry(res["assign"].reshape(E, n), e_axis_last=False)
-    res["top2_idx"] = to_entry(res["top2_idx"].reshape(n, _abi.TW_K, E))
-    if want_topk:
-        res["topk_idx"] = to_entry(res["topk_idx"].reshape(n, _abi.TW_K, E))
+    res = to_caller_order({k: v.cpu().numpy() for k, v in out.items()}, order, n, E, want_topk)
     res.update(time_windows=wins, skip_budget=budgets, skip_count=counts, pair_params=pair, large_delay=large_delay,
                sorted_order=order)
     return res
