@@ -483,30 +483,54 @@ def exact_mwis(cands):
     the first in depth-first order (in-spans ascending, ranks ascending, "unassigned" last) wins."""
     nw = len(cands)
     w = [[int((WEIGHT_OFFSET + s) * MWIS_FIXED_SCALE) for s, _ in c] for c in cands]
-    ub = [0] * (nw + 1)
-    for k in range(nw - 1, -1, -1):
-        ub[k] = ub[k + 1] + max([0] + w[k])
-    best = [-1, [-1] * nw]
-    cur = [-1] * nw
 
     def conflict(a, ra, b, rb):
         return any(x == y for x, y in zip(cands[a][ra][1], cands[b][rb][1]))
 
-    def rec(k, tot):
-        if k == nw:
-            if tot > best[0]:
-                best[0], best[1] = tot, list(cur)
-            return
-        if tot + ub[k] <= best[0]:
-            return
-        for r in range(len(cands[k])):
-            if not w[k][r] > 0:
-                continue
-            if any(cur[a] >= 0 and conflict(a, cur[a], k, r) for a in range(k)):
-                continue
-            cur[k] = r
-            rec(k + 1, tot + w[k][r])
-        cur[k] = -1
-        rec(k + 1, tot)
-    rec(0, 0)
-    return best[1]
+    # connected components of the in-span conflict graph are independent instances; solving them one
+    # by one (members ascending) gives the same set as one depth-first search over the whole window
+    adj = [[any(conflict(a, ra, b, rb) for ra in range(len(cands[a])) for rb in range(len(cands[b])))
+            if a != b else False for b in range(nw)] for a in range(nw)]
+    chosen = [-1] * nw
+    seen = [False] * nw
+    for seed in range(nw):
+        if seen[seed]:
+            continue
+        comp, stack = [], [seed]
+        seen[seed] = True
+        while stack:
+            k = stack.pop()
+            comp.append(k)
+            for j in range(nw):
+                if adj[k][j] and not seen[j]:
+                    seen[j] = True
+                    stack.append(j)
+        comp.sort()
+        m = len(comp)
+        ub = [0] * (m + 1)
+        for l in range(m - 1, -1, -1):
+            ub[l] = ub[l + 1] + max([0] + w[comp[l]])
+        best = [-1, [-1] * m]
+        cur = [-1] * m
+
+        def rec(l, tot):
+            if l == m:
+                if tot > best[0]:
+                    best[0], best[1] = tot, list(cur)
+                return
+            if tot + ub[l] <= best[0]:
+                return
+            k = comp[l]
+            for r in range(len(cands[k])):
+                if not w[k][r] > 0:
+                    continue
+                if any(cur[a] >= 0 and conflict(comp[a], cur[a], k, r) for a in range(l)):
+                    continue
+                cur[l] = r
+                rec(l + 1, tot + w[k][r])
+            cur[l] = -1
+            rec(l + 1, tot)
+        rec(0, 0)
+        for l, k in enumerate(comp):
+            chosen[k] = best[1][l]
+    return chosen

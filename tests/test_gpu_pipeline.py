@@ -154,8 +154,12 @@ def test_unsupported_modes_fail_loudly(predictor):
     in_parts, out_parts, truth, G = reference_call_args(g)
     with pytest.raises(NotImplementedError):
         predictor.FindAssignments("MaxScoreBatchParallel", g.meta["process"], in_parts, out_parts, True, [], truth, G)
+    with pytest.raises(NotImplementedError):   # the true-skips / true-distribution ablations (executor.py:1176-1183)
+        predictor.FindAssignments("MaxScoreBatchSubsetWithSkips", g.meta["process"], in_parts, out_parts, False, [],
+                                  truth, G, True, False)
+    # a service with a skip budget (one outgoing span missing) is solved, not rejected (tests/test_skip_mode.py)
     ep = list(out_parts)[0]
     out_parts[ep] = out_parts[ep][:-1]
-    with pytest.raises(NotImplementedError):
-        predictor.FindAssignments("MaxScoreBatchSubsetWithSkips", g.meta["process"], in_parts, out_parts, False, [],
-                                  truth, G)
+    res = predictor.FindAssignments("MaxScoreBatchSubsetWithSkips", g.meta["process"], in_parts, out_parts, False, [],
+                                    truth, G)
+    assert len(res) == 6 and res[3] == len(list(in_parts.values())[0])

@@ -150,32 +150,46 @@ def test_engine_equals_reference(path):
     _check_against_golden(g, res, exact_scores=False)
 
 
+def synthetic_two_skip_eps(seed=5, n=240):
+    """A service with cache hits on TWO of three parallel callees (skip spans at two tuple positions,
+    which no shipped dataset has; the third callee is complete, so no tuple is all-skip — on that the
+    reference itself raises)."""
+    rng = np.random.default_rng(seed)
+    in_s = np.cumsum(rng.integers(2000, 9000, n)).astype(np.int64) + 1_600_000_000_000_000
+    in_e = in_s + rng.integers(9000, 16000, n)
+    outs_s, outs_e = [], []
+    for e, missing in enumerate((30, 17, 0)):
+        s = in_s + rng.integers(200, 3000, n)
+        en = s + rng.integers(1000, 4000, n)
+        keep = np.sort(rng.choice(n, n - missing, replace=False))
+        s, en = s[keep], en[keep]
+        od = np.argsort(s, kind="stable")
+        outs_s.append(s[od])
+        outs_e.append(en[od])
+    return in_s, in_e, outs_s, outs_e, [[], [], []]
+
+
+def test_device_code_on_cpu_equals_oracle_on_two_skip_eps():
+    import emul_backend
+    in_s, in_e, outs_s, outs_e, preds = synthetic_two_skip_eps()
+    ref = osk.solve_skip(in_s, in_e, outs_s, outs_e, preds)
+    res = emul_backend.skip_solve(in_s, in_e, outs_s, outs_e, preds, ref["time_windows"], ref["skip_count"],
+                                  ref["pair_params"], ref["skip_budget"])
+    for a, b in (("top2_idx", "topk2_idx"), ("topk_idx", "topk_idx"), ("mis_rank", "mis_rank"), ("assign", "assign")):
+        assert np.array_equal(res[a], ref[b]), a
+    assert ((res["assign"] == -2).sum(axis=1) > 0).tolist() == [True, True, False]
+
+
 @pytest.mark.gpu
 def test_engine_equals_oracle_on_synthetic_skips():
-    """A generated service with cache hits on TWO eps (skip spans at two tuple positions, which no shipped
-    dataset has): engine == oracle, index for index."""
     from traceweaver_b200.engine import Engine
-    rng = np.random.default_rng(5)
-    n = 240
-    in_s = np.cumsum(rng.integers(2000, 9000, n)).astype(np.int64) + 1_600_000_000_000_000
-    dur = rng.integers(20000, 40000, n)
-    in_e = in_s + dur
-    o0s = in_s + rng.integers(200, 900, n)
-    o0e = o0s + rng.integers(3000, 6000, n)
-    o1s = o0e + rng.integers(200, 900, n)
-    o1e = o1s + rng.integers(3000, 6000, n)
-    keep0 = np.sort(rng.choice(n, n - 30, replace=False))
-    keep1 = np.sort(rng.choice(n, n - 17, replace=False))
-    outs_s = [np.sort(o0s[keep0]), o1s[keep1]]
-    outs_e = [o0e[keep0][np.argsort(o0s[keep0], kind="stable")], o1e[keep1]]
-    od = np.argsort(outs_s[1], kind="stable")
-    outs_s[1], outs_e[1] = outs_s[1][od], outs_e[1][od]
-    preds = [[], [0]]
+    in_s, in_e, outs_s, outs_e, preds = synthetic_two_skip_eps()
     ref = osk.solve_skip(in_s, in_e, outs_s, outs_e, preds)
     eng = Engine(0)
     res = skipmode.solve(eng, in_s, in_e, outs_s, outs_e, preds)
     eng.close()
     assert np.array_equal(res["skip_count"], np.asarray(ref["skip_count"]))
+    assert np.array_equal(res["pair_params"], ref["pair_params"], equal_nan=True)
     assert np.array_equal(res["top2_idx"], ref["topk2_idx"])
     assert np.array_equal(res["topk_idx"], ref["topk_idx"])
     assert np.array_equal(res["mis_rank"], ref["mis_rank"])
