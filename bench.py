@@ -114,22 +114,13 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def accuracy(assign, truth, hb):
+def accuracy(eng, assign, truth, hb):
     """Fraction of incoming spans whose children are all assigned correctly (AccuracyForService,
-    helpers/utils.py:62-79, on index arrays), computed on the device."""
-    import torch
-    ok = (assign == truth)
-    tot, good = 0, 0
-    E_of = np.diff(hb.prob_ep_off)
-    n_of = np.diff(hb.prob_in_off)
-    for E in np.unique(E_of):
-        for n in np.unique(n_of[E_of == E]):
-            sel = np.flatnonzero((E_of == E) & (n_of == n))
-            offs = torch.as_tensor(hb.prob_tuple_off[sel], device=ok.device)
-            idx = offs[:, None] + torch.arange(int(E) * int(n), device=ok.device)[None, :]
-            good += int(ok[idx].reshape(len(sel), int(E), int(n)).all(dim=1).sum().item())
-            tot += len(sel) * int(n)
-    return good / max(tot, 1)
+    helpers/utils.py:62-79, on index arrays), computed on the device by tw_accuracy (csrc/tw_truth.cu)."""
+    from traceweaver_b200 import truth as dev_truth
+    tl = dev_truth.TraceLists.from_host_batch(hb, None, 0)
+    a = dev_truth.accuracy(eng, tl, truth, assign, resident=eng.d)
+    return float(a["correct"].sum()) / max(int(a["n_in"].sum()), 1)
 
 
 def physical_cores():
@@ -269,7 +260,7 @@ def measure(args, blocks, hb, dev_index, steps, warmup, gather=None, rank=0, wor
         sampler.finish()
     resident_ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = eng.launch_count() - l0
-    acc = accuracy(res["assign"], truth, hb)
+    acc = accuracy(eng, res["assign"], truth, hb)
     unassigned = int(res["counters"][:, 1].sum().item())
     gather_ok = None
     if gather is not None:

@@ -304,6 +304,42 @@ int tw_skip_solve(tw_engine* eng, const tw_batch* dev, const tw_batch* host_desc
 int tw_build_dist_samples(tw_engine* eng, int32_t n, const int64_t* start, const int64_t* end, const int8_t* label,
                           int32_t E, int64_t large_delay, int32_t* key_out, int64_t* val_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Ground truth, invocation order and accuracy on the device.  All three are
+ * joins on the trace id; the loader numbers the traces densely.  These entry points read only the
+ * offset tables and the out_start / out_end arrays of `dev` / `host_desc` (ep_term_off, ep_pred_mask,
+ * term_src may be NULL: the callee order is not known yet when the truth is derived).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tw_trace_keys {
+  const int32_t* in_trace;      /* [n_in_total]  trace number of every incoming span (device)            */
+  const int32_t* out_trace;     /* [n_out_total] trace number of every outgoing span (device)            */
+  const int32_t* prob_trace_lo; /* [P] smallest trace number among problem p's incoming spans (device)   */
+  const int32_t* prob_trace_n;  /* [P] 1 + largest - smallest (device)                                   */
+  int32_t n_traces;             /* every trace number is < n_traces                                      */
+  int32_t reserved0;
+} tw_trace_keys;
+
+/* utils.GetGroundTruth (helpers/utils.py:22-32): truth_out[tuple_off[p] + e*n_p + i] = position of the FIRST
+ * span of callee e's list that carries in-span i's trace id, -1 if none.  host_trace_n: HOST copy of
+ * prob_trace_n (sizes the join tables). */
+int tw_ground_truth(tw_engine* eng, const tw_batch* dev, const tw_batch* host_desc, const tw_trace_keys* keys,
+                    const int32_t* host_trace_n, int32_t* truth_out, void* stream);
+
+/* FindOrder (executor.py:214-285): violated_out[ep0_p + a] has bit b set iff some in-span's true child at
+ * callee a ends after its true child at callee b starts, i.e. the edge a -> b of the complete digraph is
+ * removed.  TW_ERR_INVALID if an in-span has no child at some callee (KeyError in the reference). */
+int tw_find_order(tw_engine* eng, const tw_batch* dev, const tw_batch* host_desc, const int32_t* truth,
+                  uint32_t* violated_out, void* stream);
+
+/* helpers/utils.py:62-145 on index arrays.  per_prob_out[p] = {in-spans right at every callee, in-spans
+ * with some rank of topk_idx right at every callee}; e2e_out = {traces seen, traces right, traces seen,
+ * traces right within the top K}.  prob_first[p] != 0 marks the services TopKAccuracyEndToEnd visits FIRST
+ * (there the last in-span of a trace decides, later services can only clear it; utils.py:118-143).
+ * topk_idx / topk_cnt / in_trace / prob_first may be NULL. */
+int tw_accuracy(tw_engine* eng, const tw_batch* dev, const tw_batch* host_desc, const int32_t* truth,
+                const int32_t* assign, const int32_t* topk_idx, const uint8_t* topk_cnt, const int32_t* in_trace,
+                int32_t n_traces, const uint8_t* prob_first, uint64_t* per_prob_out, uint64_t* e2e_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,7 @@ def test_struct_layout_matches_header(lib):
     assert C.sizeof(_abi.TwPassOut) == 7 * 8
     assert C.sizeof(_abi.TwScoreOut) == 9 * 8
     assert C.sizeof(_abi.TwSkipDesc) == 10 * 8
+    assert C.sizeof(_abi.TwTraceKeys) == 4 * 8 + 8
     assert C.sizeof(_abi.TwSkipOut) == 7 * 8 + 4 * 8
 
 

@@ -24,6 +24,16 @@ def test_trace_directory_to_assignments(tmp_path):
         _write_traces(blk, 0, str(d), [f"svc{q}_{e}" for e in range(len(blk.out_start))])
         loaded = load_jaeger_dir(str(d))
         assert len(loaded) == 1
+        # ground truth + FindOrder derived on the device (row f-2) == the NumPy derivation
+        from traceweaver_b200.engine import Engine
+        eng = Engine(0)
+        on_dev = load_jaeger_dir(str(d), engine=eng)
+        eng.close()
+        assert len(on_dev) == 1 and on_dev[0].out_eps == loaded[0].out_eps
+        assert np.array_equal(on_dev[0].truth, loaded[0].truth)
+        assert on_dev[0].graph_edges == loaded[0].graph_edges and on_dev[0].problem.preds == loaded[0].problem.preds
+        for a, b in zip(on_dev[0].problem.out_start, loaded[0].problem.out_start):
+            assert np.array_equal(a, b)
         services += loaded
     hb = to_host_batch(services)
     solver = BatchSolver(device=0, seed_select=10)

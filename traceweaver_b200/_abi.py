@@ -67,6 +67,11 @@ class TwSkipOut(C.Structure):
     _fields_ = [("pass_", TwPassOut), ("top2_score", P), ("top2_idx", P), ("top2_cnt", P), ("cut", P)]
 
 
+class TwTraceKeys(C.Structure):
+    _fields_ = [("in_trace", P), ("out_trace", P), ("prob_trace_lo", P), ("prob_trace_n", P),
+                ("n_traces", C.c_int32), ("reserved0", C.c_int32)]
+
+
 class TwError(RuntimeError):
     def __init__(self, code, where, detail=""):
         self.code = code

@@ -55,6 +55,13 @@ struct tw_engine {
   uint8_t* own_used_wide = nullptr;
   uint32_t* taken = nullptr;
   size_t taken_words = 0;
+  // ground truth / order / accuracy scratch (tw_truth.cu)
+  int32_t* truth_tab = nullptr;
+  int64_t* truth_tab_off = nullptr;
+  int32_t* in_prob = nullptr;
+  int* order_missing = nullptr;
+  uint8_t* acc_flags = nullptr;
+  unsigned long long* acc_first = nullptr;
   // skip / cache mode scratch (tw_skip_solve)
   uint32_t* skip_sets = nullptr;
   int64_t* skip_set_off = nullptr;
@@ -387,6 +394,92 @@ int tw_build_dist_samples(tw_engine* eng, int32_t n, const int64_t* start, const
   CU(cudaSetDevice(eng->device));
   CU(launch_build_dist(n, start, end, label, E, large_delay, key_out, val_out, (cudaStream_t)stream_));
   eng->launches += 1;
+  return TW_OK;
+}
+
+static int offsets_ok(const tw_batch* h, const char* who) {
+  if (!h || h->n_problems < 1 || !h->prob_in_off || !h->prob_ep_off || !h->prob_tuple_off || !h->ep_out_off)
+    return fail(TW_ERR_INVALID, "%s: NULL offset table", who);
+  const int P = h->n_problems;
+  for (int p = 0; p < P; ++p) {
+    const int E = h->prob_ep_off[p + 1] - h->prob_ep_off[p];
+    const int64_t n = h->prob_in_off[p + 1] - h->prob_in_off[p];
+    if (E < 1 || E > TW_MAX_E || n < 1 || h->prob_tuple_off[p + 1] - h->prob_tuple_off[p] != n * E)
+      return fail(TW_ERR_INVALID, "%s: inconsistent offsets", who);
+  }
+  if (h->prob_in_off[P] != h->n_in_total || h->prob_ep_off[P] != h->n_ep_total ||
+      h->ep_out_off[h->n_ep_total] != h->n_out_total)
+    return fail(TW_ERR_INVALID, "%s: totals inconsistent", who);
+  return TW_OK;
+}
+
+int tw_ground_truth(tw_engine* eng, const tw_batch* dev, const tw_batch* h, const tw_trace_keys* keys,
+                    const int32_t* host_trace_n, int32_t* truth_out, void* stream_) {
+  if (!eng || !dev || !keys || !host_trace_n || !truth_out) return fail(TW_ERR_INVALID, "tw_ground_truth: NULL argument");
+  int rc = offsets_ok(h, "tw_ground_truth");
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream_;
+  CU(cudaSetDevice(eng->device));
+  const int P = h->n_problems;
+  std::vector<int64_t> tab_off((size_t)P + 1, 0);
+  for (int p = 0; p < P; ++p) {
+    if (host_trace_n[p] < 0) return fail(TW_ERR_INVALID, "tw_ground_truth: negative trace range");
+    tab_off[p + 1] = tab_off[p] + (int64_t)(h->prob_ep_off[p + 1] - h->prob_ep_off[p]) * host_trace_n[p];
+  }
+  if (tab_off[P] > (int64_t)1 << 32) return fail(TW_ERR_RANGE_LIMIT, "tw_ground_truth: trace numbers of a service are too sparse");
+  CU(eng->alloc(&eng->truth_tab, (size_t)tab_off[P]));
+  CU(eng->alloc(&eng->truth_tab_off, (size_t)P + 1));
+  CU(eng->alloc(&eng->in_prob, (size_t)h->n_in_total));
+  CU(cudaMemcpyAsync(eng->truth_tab_off, tab_off.data(), tab_off.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  CU(launch_in_prob(*dev, eng->in_prob, s));
+  CU(launch_ground_truth(*dev, keys->in_trace, keys->out_trace, keys->prob_trace_lo, keys->prob_trace_n, eng->truth_tab_off,
+                         tab_off[P], eng->truth_tab, eng->in_prob, truth_out, s));
+  CU(cudaStreamSynchronize(s));    // tab_off goes out of scope
+  eng->launches += 3;
+  return TW_OK;
+}
+
+int tw_find_order(tw_engine* eng, const tw_batch* dev, const tw_batch* h, const int32_t* truth, uint32_t* violated_out,
+                  void* stream_) {
+  if (!eng || !dev || !truth || !violated_out) return fail(TW_ERR_INVALID, "tw_find_order: NULL argument");
+  int rc = offsets_ok(h, "tw_find_order");
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream_;
+  CU(cudaSetDevice(eng->device));
+  CU(eng->alloc(&eng->in_prob, (size_t)h->n_in_total));
+  CU(eng->alloc(&eng->order_missing, 1));
+  CU(launch_in_prob(*dev, eng->in_prob, s));
+  CU(launch_find_order(*dev, truth, eng->in_prob, violated_out, eng->order_missing, s));
+  int missing = 0;
+  CU(cudaMemcpyAsync(&missing, eng->order_missing, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  eng->launches += 2;
+  if (missing) return fail(TW_ERR_INVALID, "tw_find_order: an incoming span has no child at some callee%s", "");
+  return TW_OK;
+}
+
+int tw_accuracy(tw_engine* eng, const tw_batch* dev, const tw_batch* h, const int32_t* truth, const int32_t* assign,
+                const int32_t* topk_idx, const uint8_t* topk_cnt, const int32_t* in_trace, int32_t n_traces,
+                const uint8_t* prob_first, uint64_t* per_prob_out, uint64_t* e2e_out, void* stream_) {
+  if (!eng || !dev || !truth || !assign || !per_prob_out || !e2e_out) return fail(TW_ERR_INVALID, "tw_accuracy: NULL argument");
+  if ((topk_idx != nullptr) != (topk_cnt != nullptr)) return fail(TW_ERR_INVALID, "tw_accuracy: topk_idx and topk_cnt go together");
+  int rc = offsets_ok(h, "tw_accuracy");
+  if (rc) return rc;
+  if (n_traces < 0 || !in_trace) n_traces = 0;
+  cudaStream_t s = (cudaStream_t)stream_;
+  CU(cudaSetDevice(eng->device));
+  CU(eng->alloc(&eng->in_prob, (size_t)h->n_in_total));
+  CU(eng->alloc(&eng->acc_flags, (size_t)3 * (size_t)n_traces + 8));
+  CU(eng->alloc(&eng->acc_first, (size_t)n_traces + 1));
+  CU(cudaMemsetAsync(eng->acc_flags, 0, (size_t)3 * (size_t)n_traces + 1, s));
+  CU(cudaMemsetAsync(eng->acc_first, 0, ((size_t)n_traces + 1) * sizeof(unsigned long long), s));
+  CU(cudaMemsetAsync(per_prob_out, 0, (size_t)h->n_problems * 2 * sizeof(uint64_t), s));
+  CU(cudaMemsetAsync(e2e_out, 0, 4 * sizeof(uint64_t), s));
+  CU(launch_in_prob(*dev, eng->in_prob, s));
+  CU(launch_accuracy(*dev, truth, assign, topk_idx, topk_cnt, n_traces ? in_trace : nullptr, eng->in_prob, prob_first,
+                     n_traces, (unsigned long long*)per_prob_out, eng->acc_flags, eng->acc_first,
+                     (unsigned long long*)e2e_out, s));
+  eng->launches += 3;
   return TW_OK;
 }
 

@@ -93,4 +93,15 @@ cudaError_t launch_skip(const tw_batch& b, const tw_skip_desc& sd, const tw_skip
 cudaError_t launch_build_dist(int n, const int64_t* ms, const int64_t* me, const int8_t* label, int E,
                               int64_t large_delay, int32_t* key, int64_t* val, cudaStream_t s);
 
+cudaError_t launch_in_prob(const tw_batch& b, int32_t* in_prob, cudaStream_t s);
+cudaError_t launch_ground_truth(const tw_batch& b, const int32_t* in_trace, const int32_t* out_trace,
+                                const int32_t* trace_lo, const int32_t* trace_n, const int64_t* tab_off, int64_t tab_len,
+                                int32_t* tab, const int32_t* in_prob, int32_t* truth, cudaStream_t s);
+cudaError_t launch_find_order(const tw_batch& b, const int32_t* truth, const int32_t* in_prob, uint32_t* violated,
+                              int* missing, cudaStream_t s);
+cudaError_t launch_accuracy(const tw_batch& b, const int32_t* truth, const int32_t* assign, const int32_t* topk_idx,
+                            const uint8_t* topk_cnt, const int32_t* in_trace, const int32_t* in_prob,
+                            const uint8_t* prob_first, int n_traces, unsigned long long* per_prob, uint8_t* flags,
+                            unsigned long long* trace_first, unsigned long long* out4, cudaStream_t s);
+
 }  // namespace tw

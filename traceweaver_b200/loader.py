@@ -204,8 +204,10 @@ def _nodes_media(d, path):
 
 
 def load_jaeger_dir(directory: str, first_span: Optional[str] = HOTEL_FIRST_SPAN, max_traces: int = MAX_TRACES,
-                    files: Optional[Sequence[str]] = None, layout: str = "hotel") -> List[ServiceProblem]:
+                    files: Optional[Sequence[str]] = None, layout: str = "hotel", engine=None) -> List[ServiceProblem]:
     """All solvable services of a trace directory, in the order the reference visits them.
+    engine: a traceweaver_b200.engine.Engine -> the ground truth and FindOrder of all services are derived
+    on the device in one batch (row f-2); None -> NumPy on the host (same result).
     layout "hotel": spans as recorded (`--fix 2`); "media": FixSpans2 rewrite (`--fix 1`, first span
     "ComposeReview"); "node": FixSpans rewrite (`--fix 0`, first span "init-span")."""
     if layout not in ("hotel", "media", "node"):
@@ -260,14 +262,16 @@ def load_jaeger_dir(directory: str, first_span: Optional[str] = HOTEL_FIRST_SPAN
         if cnt > max_traces:
             break
 
-    services = []
+    lists = []
     for process, o in outs.items():                                                      # executor.py:1080
         if not o.start or process not in ins:
             continue
-        sp = _service_problem(process, ins[process], o)
-        if sp is not None:
-            services.append(sp)
-    return services
+        L = _service_lists(process, ins[process], o)
+        if L is not None:
+            lists.append(L)
+    if engine is not None and lists:
+        return _services_device(engine, lists)
+    return [_finish_service(L, *_truth_and_order_host(L)) for L in lists]
 
 
 def _partition(rows: _Rows):
@@ -285,24 +289,48 @@ def _partition(rows: _Rows):
     return parts, start, end
 
 
-def _service_problem(process, i_rows: _Rows, o_rows: _Rows) -> Optional[ServiceProblem]:
-    import networkx as nx
+def _service_lists(process, i_rows: _Rows, o_rows: _Rows):
+    """Partitions of one service (executor.py:1100-1128): None when it has more than one incoming endpoint."""
     in_parts, i_start, i_end = _partition(i_rows)
     out_parts, o_start, o_end = _partition(o_rows)
     if len(in_parts) > 1:
         return None                                                                      # "SKIPPING THIS PROCESS", :1121
     in_ep, in_idx = next(iter(in_parts.items()))
     given = list(out_parts.keys())
-    n = len(in_idx)
-    i_tid = np.asarray(i_rows.tid)[in_idx]
-    # ground truth: the first span of the partition with the in-span's trace id (utils.py:22-32)
+    return dict(process=process, in_ep=in_ep, in_idx=in_idx, given=given, out_parts=out_parts,
+                i_start=i_start, i_end=i_end, o_start=o_start, o_end=o_end, i_rows=i_rows, o_rows=o_rows,
+                i_tid=np.asarray(i_rows.tid)[in_idx])
+
+
+def _truth_and_order_host(L):
+    """GetGroundTruth (utils.py:22-32) and FindOrder's pruning (executor.py:248-266) in NumPy: the truth
+    [E, n] in the given callee order and, per callee a, the bit mask of callees b whose edge a -> b some
+    trace violates (x.end > y.start)."""
+    given, out_parts, o_rows = L["given"], L["out_parts"], L["o_rows"]
+    n = len(L["in_idx"])
     truth_given = np.full((len(given), n), -1, np.int32)
     for g, ep in enumerate(given):
         first: Dict[str, int] = {}
         for pos, k in enumerate(out_parts[ep]):
             first.setdefault(o_rows.tid[k], pos)
-        truth_given[g] = [first.get(t, -1) for t in i_tid]
-    # FindOrder (executor.py:214-285): complete digraph minus every order some trace violates
+        truth_given[g] = [first.get(t, -1) for t in L["i_tid"]]
+    if (truth_given < 0).any():
+        raise ValueError(f"{L['process']}: an in-span has no child at some callee (FindOrder would raise KeyError)")
+    ts = np.stack([L["o_start"][out_parts[ep]][truth_given[g]] for g, ep in enumerate(given)])     # [E, n]
+    te = np.stack([L["o_end"][out_parts[ep]][truth_given[g]] for g, ep in enumerate(given)])
+    violated = [0] * len(given)
+    for a in range(len(given)):
+        for b in range(len(given)):
+            if a != b and bool((te[a] > ts[b]).any()):
+                violated[a] |= 1 << b
+    return truth_given, violated
+
+
+def _finish_service(L, truth_given, violated) -> ServiceProblem:
+    """FindOrder's graph (complete digraph minus the violated edges, executor.py:214-285), the
+    topological callee order (traceweaver_v1.py:37-39) and the index-only problem."""
+    import networkx as nx
+    given, out_parts = L["given"], L["out_parts"]
     G = nx.DiGraph()
     for ep in given:
         G.add_node(ep)
@@ -310,27 +338,60 @@ def _service_problem(process, i_rows: _Rows, o_rows: _Rows) -> Optional[ServiceP
         for b in given:
             if a != b:
                 G.add_edge(a, b)
-    if (truth_given < 0).any():
-        raise ValueError(f"{process}: an in-span has no child at some callee (FindOrder would raise KeyError)")
-    ts = np.stack([o_start[out_parts[ep]][truth_given[g]] for g, ep in enumerate(given)])     # [E, n]
-    te = np.stack([o_end[out_parts[ep]][truth_given[g]] for g, ep in enumerate(given)])
     for a in range(len(given)):
         for b in range(len(given)):
-            if a != b and G.has_edge(given[a], given[b]) and bool((te[a] > ts[b]).any()):
+            if a != b and (violated[a] >> b & 1) and G.has_edge(given[a], given[b]):
                 G.remove_edge(given[a], given[b])                                        # x.end > y.start (:250, :262)
     topo = list(nx.topological_sort(G))                                                  # traceweaver_v1.py:37-39
     pos = {ep: e for e, ep in enumerate(topo)}
     g_of = [given.index(ep) for ep in topo]
     preds = [[pos[b] for b, _ in G.in_edges(ep)] for ep in topo]
     out_idx = [out_parts[ep] for ep in topo]
-    prob = Problem(in_start=i_start[in_idx], in_end=i_end[in_idx],
-                   out_start=[o_start[ix] for ix in out_idx], out_end=[o_end[ix] for ix in out_idx],
-                   preds=preds, name=process)
+    i_rows, o_rows, in_idx = L["i_rows"], L["o_rows"], L["in_idx"]
+    prob = Problem(in_start=L["i_start"][in_idx], in_end=L["i_end"][in_idx],
+                   out_start=[L["o_start"][ix] for ix in out_idx], out_end=[L["o_end"][ix] for ix in out_idx],
+                   preds=preds, name=L["process"])
     return ServiceProblem(
-        name=process, in_ep=in_ep, out_eps_given=given, out_eps=topo, problem=prob,
+        name=L["process"], in_ep=L["in_ep"], out_eps_given=given, out_eps=topo, problem=prob,
         in_ids=[(i_rows.tid[k], i_rows.sid[k]) for k in in_idx],
         out_ids=[[(o_rows.tid[k], o_rows.sid[k]) for k in ix] for ix in out_idx],
-        truth=np.ascontiguousarray(truth_given[g_of]), graph_edges=list(G.edges()))
+        truth=np.ascontiguousarray(np.asarray(truth_given)[g_of]), graph_edges=list(G.edges()))
+
+
+def _service_problem(process, i_rows: _Rows, o_rows: _Rows) -> Optional[ServiceProblem]:
+    L = _service_lists(process, i_rows, o_rows)
+    if L is None:
+        return None
+    truth_given, violated = _truth_and_order_host(L)
+    return _finish_service(L, truth_given, violated)
+
+
+def _services_device(engine, lists) -> List[ServiceProblem]:
+    """Ground truth and FindOrder of all services in ONE batch on the device (tw_ground_truth,
+    tw_find_order: joins on the densely numbered trace id, csrc/tw_truth.cu); the per-service graphs
+    (a handful of nodes) are then built on the host as before."""
+    from . import truth as dev_truth
+    number: Dict[str, int] = {}
+    in_tr, out_tr, probs = [], [], []
+    for L in lists:
+        in_tr.append(np.fromiter((number.setdefault(t, len(number)) for t in L["i_tid"]), np.int32, len(L["i_tid"])))
+        o_tid = L["o_rows"].tid
+        out_tr.append([np.fromiter((number.setdefault(o_tid[k], len(number)) for k in L["out_parts"][ep]), np.int32,
+                                   len(L["out_parts"][ep])) for ep in L["given"]])
+        probs.append(dict(in_start=L["i_start"][L["in_idx"]], in_end=L["i_end"][L["in_idx"]],
+                          out_start=[L["o_start"][L["out_parts"][ep]] for ep in L["given"]],
+                          out_end=[L["o_end"][L["out_parts"][ep]] for ep in L["given"]]))
+    tl = dev_truth.TraceLists(probs, in_tr, out_tr, len(number))
+    truth = dev_truth.ground_truth(engine, tl)
+    violated = dev_truth.find_order(engine, tl, truth)
+    truth = truth.cpu().numpy()
+    out = []
+    for p, L in enumerate(lists):
+        E, n = len(L["given"]), len(L["in_idx"])
+        t0 = int(tl.arrays["prob_tuple_off"][p])
+        e0 = int(tl.arrays["prob_ep_off"][p])
+        out.append(_finish_service(L, truth[t0:t0 + E * n].reshape(E, n), [int(v) for v in violated[e0:e0 + E]]))
+    return out
 
 
 def to_host_batch(services: Sequence[ServiceProblem], skipped: list = None):
