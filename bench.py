@@ -414,6 +414,12 @@ def run_ours(args):
 
     rank, local_rank, world = dist_env()
     torch.cuda.set_device(local_rank)
+    # torchrun exports OMP_NUM_THREADS=1; the end-to-end leg copies ~0.5 GB of caller arrays into pinned
+    # staging on the host every step, which torch does with its intra-op threads: give every rank its share
+    try:
+        torch.set_num_threads(max(1, len(physical_cores()) // max(world, 1)))
+    except RuntimeError:
+        pass
     if world > 1:
         # stdout carries the one JSON line only: NCCL prints its version banner with printf when the
         # first communicator is created, so stdout points at stderr until that has happened

@@ -254,6 +254,14 @@ int tw_gmm_stream_draws(tw_engine* eng, const int64_t* term_sample_off, const do
                         const int32_t* counts, uint32_t* prob_draws_out, void* stream);
 
 
+/* Measurement aids of the refit's FP64 roofline (bench.py: roofline_refit).
+ * tw_gmm_work: sample-component evaluations the EM sweeps of tw_gmm_refit have performed since the last
+ * reset (one E+M sweep of a K-component fit over n samples counts n*K); blocks until the device is idle.
+ * tw_measure_fp64_peak: dense FP64 FMA issue rate of the device in TFLOP/s (8 independent DFMA chains
+ * per thread, timed with CUDA events) — the builder-measured peak the refit is quoted against. */
+int tw_gmm_work(tw_engine* eng, uint64_t* em_evals_out, int reset);
+int tw_measure_fp64_peak(tw_engine* eng, double* tflops_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Skip / cache mode.  A service some of whose outgoing lists do not
  * hold one span per incoming span (overall_skip_budget != 0, traceweaver_v3.py:1138-1158 — cache hits,

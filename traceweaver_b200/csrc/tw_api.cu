@@ -397,6 +397,47 @@ int tw_build_dist_samples(tw_engine* eng, int32_t n, const int64_t* start, const
   return TW_OK;
 }
 
+int tw_gmm_work(tw_engine* eng, uint64_t* em_evals_out, int reset) {
+  if (!eng || !em_evals_out) return fail(TW_ERR_INVALID, "tw_gmm_work: NULL argument");
+  CU(cudaSetDevice(eng->device));
+  CU(cudaDeviceSynchronize());
+  unsigned long long v = 0;
+  CU(gmm_work_read(&v, reset != 0));
+  *em_evals_out = v;
+  return TW_OK;
+}
+
+int tw_measure_fp64_peak(tw_engine* eng, double* tflops_out, void* stream_) {
+  if (!eng || !tflops_out) return fail(TW_ERR_INVALID, "tw_measure_fp64_peak: NULL argument");
+  cudaStream_t s = (cudaStream_t)stream_;
+  CU(cudaSetDevice(eng->device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, eng->device));
+  double* sink = nullptr;
+  CU(eng->alloc(&sink, 1));
+  const int blocks = prop.multiProcessorCount * 8, iters = 1 << 15;
+  cudaEvent_t a, b;
+  CU(cudaEventCreate(&a));
+  CU(cudaEventCreate(&b));
+  CU(launch_fp64_peak(blocks, 1 << 10, sink, s));            // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    CU(cudaEventRecord(a, s));
+    CU(launch_fp64_peak(blocks, iters, sink, s));
+    CU(cudaEventRecord(b, s));
+    CU(cudaEventSynchronize(b));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, a, b));
+    const double flops = 2.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  *tflops_out = best;
+  return TW_OK;
+}
+
 static int offsets_ok(const tw_batch* h, const char* who) {
   if (!h || h->n_problems < 1 || !h->prob_in_off || !h->prob_ep_off || !h->prob_tuple_off || !h->ep_out_off)
     return fail(TW_ERR_INVALID, "%s: NULL offset table", who);

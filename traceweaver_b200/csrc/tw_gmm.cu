@@ -58,6 +58,10 @@ __device__ unsigned long long g_gmm_phase[16];
 #define TW_GCOUNT(k, v) do { } while (0)
 #endif
 
+// Work of the EM sweeps (always on; one atomic per fit): sample-component evaluations of the E+M sweep.
+// bench.py turns it into the FP64 roofline of the refit (tw_gmm_work, include/traceweaver_b200.h).
+__device__ unsigned long long g_gmm_em_evals;
+
 __device__ __forceinline__ double wsum(double v) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
@@ -462,6 +466,7 @@ __device__ __forceinline__ bool em_fit(const double* __restrict__ x, int n, doub
   if (!params_from_stats<FULL>(f, k, n, nk, mup, S2, shift, true)) return false;
   TW_GPHASE(2);
   double lower = -INFINITY;
+  int em_sweeps = 0;
   for (int it = 1; it <= kEmMaxIter; ++it) {
     const double prev = lower;
     LogSum ls;
@@ -507,10 +512,15 @@ __device__ __forceinline__ bool em_fit(const double* __restrict__ x, int n, doub
         }
       }
     }
-    if (!params_from_stats<FULL>(f, k, n, nk, mup, S2, shift, false)) return false;
+    if (!params_from_stats<FULL>(f, k, n, nk, mup, S2, shift, false)) {
+      if (lane == 0) atomicAdd(&g_gmm_em_evals, (unsigned long long)it * (unsigned long long)n * K);
+      return false;
+    }
     TW_GCOUNT(6, 1);
+    em_sweeps = it;
     if (fabs(lower - prev) < kEmTol) break;
   }
+  if (lane == 0) atomicAdd(&g_gmm_em_evals, (unsigned long long)(em_sweeps + (want_score ? 1 : 0)) * (unsigned long long)n * K);
   TW_GPHASE(3);
   if (want_score) {
     LogSum ls;
@@ -810,6 +820,36 @@ k_gmm_final(FitSel sel, const int64_t* __restrict__ term_sample_off, const doubl
 }
 
 #ifdef TW_PROFILE_PHASES
+// ---- FP64 issue-rate micro-benchmark (the peak the refit's roofline is quoted against): every thread
+// runs 8 independent DFMA chains; 2 flops per DFMA.
+__global__ void __launch_bounds__(256)
+k_fp64_peak(int iters, double* __restrict__ sink) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3, a4 = a0 + 4e-3, a5 = a0 + 5e-3,
+         a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+  const double m = 0.9999999, c = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (r == 123.456) sink[0] = r;       // never true: keeps the chains alive
+}
+
+cudaError_t launch_fp64_peak(int blocks, int iters, double* sink, cudaStream_t s) {
+  k_fp64_peak<<<blocks, 256, 0, s>>>(iters, sink);
+  return cudaGetLastError();
+}
+
+cudaError_t gmm_work_read(unsigned long long* out, bool reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_gmm_em_evals, sizeof(unsigned long long));
+  if (e != cudaSuccess) return e;
+  if (reset) {
+    const unsigned long long z = 0;
+    e = cudaMemcpyToSymbol(g_gmm_em_evals, &z, sizeof z);
+  }
+  return e;
+}
+
 extern "C" int tw_debug_gmm_phases(unsigned long long* out16, int reset) {
   cudaError_t e = cudaMemcpyFromSymbol(out16, g_gmm_phase, sizeof(unsigned long long) * 16);
   if (e != cudaSuccess) return -2;

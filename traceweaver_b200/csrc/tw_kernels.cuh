@@ -93,6 +93,8 @@ cudaError_t launch_skip(const tw_batch& b, const tw_skip_desc& sd, const tw_skip
 cudaError_t launch_build_dist(int n, const int64_t* ms, const int64_t* me, const int8_t* label, int E,
                               int64_t large_delay, int32_t* key, int64_t* val, cudaStream_t s);
 
+cudaError_t launch_fp64_peak(int blocks, int iters, double* sink, cudaStream_t s);
+cudaError_t gmm_work_read(unsigned long long* out, bool reset);
 cudaError_t launch_in_prob(const tw_batch& b, int32_t* in_prob, cudaStream_t s);
 cudaError_t launch_ground_truth(const tw_batch& b, const int32_t* in_trace, const int32_t* out_trace,
                                 const int32_t* trace_lo, const int32_t* trace_n, const int64_t* tab_off, int64_t tab_len,

@@ -199,6 +199,18 @@ class Engine:
                                                 _p(out), self.stream), "tw_gmm_stream_draws")
         return out
 
+    def gmm_work(self, reset=False):
+        """EM sample-component evaluations since the last reset (tw_gmm_work; syncs the device)."""
+        v = C.c_uint64(0)
+        _lib.check(self.lib.tw_gmm_work(self.h, C.byref(v), 1 if reset else 0), "tw_gmm_work")
+        return int(v.value)
+
+    def fp64_peak_tflops(self):
+        """Measured dense FP64 FMA rate of this device (tw_measure_fp64_peak)."""
+        v = C.c_double(0.0)
+        _lib.check(self.lib.tw_measure_fp64_peak(self.h, C.byref(v), self.stream), "tw_measure_fp64_peak")
+        return float(v.value)
+
     def delays(self, assign):
         hb = self.hb
         delays = torch.empty(int(hb.term_sample_off[-1]), dtype=torch.float64, device=self.device)

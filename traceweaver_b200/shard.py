@@ -56,9 +56,12 @@ class BlockSpec:
         return self.n_in * len(synth.SHAPES[self.shape]["eps"])
 
 
-def stream_spec(workload: str, n_services: int, n_in: int, seed: int, block_services: int = 256) -> List[BlockSpec]:
+def stream_spec(workload: str, n_services: int, n_in: int, seed: int, block_services: int = 32) -> List[BlockSpec]:
     """The global service list of a synthetic workload as small seeded blocks, so that a rank can
-    generate exactly its slice: block k is reproducible from (shape, load, seed + k) alone."""
+    generate exactly its slice: block k is reproducible from (shape, load, seed + k) alone.  Blocks are
+    short (one (shape, load) cycle = 12 blocks = 384 services for the hotel stream) so that every
+    contiguous slice of a few thousand services holds the same mix of shapes and load levels: with long
+    blocks the ranks of a partitioned list got different mixes and the slowest rank set the step time."""
     loads = (25, 50, 75, 100, 125, 150)
     if workload == "hotel":
         cycle = [(s, l, 1) for l in loads for s in ("hotel_frontend", "hotel_search")]
