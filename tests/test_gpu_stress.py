@@ -181,3 +181,26 @@ def test_engine_limits_fail_loudly(engine):
     with pytest.raises(_abi.TwError) as ei:
         engine.bind(hb)
     assert ei.value.code == -1
+
+
+def test_one_service_of_120k_spans_equals_oracle():
+    """A single service with 30 000 incoming spans (120 000 spans, lists far beyond the 16 384 spans the
+    shared-memory end-time sort takes): long lists are sorted in global memory (k_sort_ends_long), the
+    stitch warp walks all windows, the refit fits 30 000 samples per term.  Engine == oracle."""
+    import torch
+    from oracle import tw_oracle
+    from traceweaver_b200 import synth
+    from traceweaver_b200.api import BatchSolver
+    from traceweaver_b200.batch import build_batch_from_blocks
+    blk = synth.make_block("hotel_frontend", 1, 30_000, 100.0, seed=3)
+    hb = build_batch_from_blocks([blk])
+    solver = BatchSolver(device=0, seed_select=10)
+    out = solver.solve(hb)
+    solver.close()
+    ref = tw_oracle.find_assignments(hb, 10, threads=4)
+    assert np.array_equal(out["assign"], ref["assign"])
+    assert np.array_equal(out["mis_rank"], ref["mis_rank"])
+    assert np.array_equal(out["topk_idx"], ref["topk_idx"])
+    assert np.array_equal(out["counters"][:, :2], ref["counters"][:, :2])
+    truth = synth.truth_assign([blk])
+    assert (out["assign"] == truth).mean() > 0.99

@@ -68,6 +68,10 @@ struct tw_engine {
   uint32_t* skip_taken = nullptr;
   int32_t* skip_win = nullptr;
   int* err_flag = nullptr;
+  int32_t* long_seg = nullptr;       // lists longer than kSortSmemCap (sorted in global memory)
+  int n_long = 0;
+  int64_t* long_scratch = nullptr;
+  int64_t slab_len = 1;
   int64_t* in_end_sorted = nullptr;
   int64_t* out_end_sorted = nullptr;
   int32_t* batch_prob = nullptr;
@@ -291,7 +295,30 @@ int tw_engine_bind(tw_engine* eng, const tw_batch* dev, const tw_batch* h, void*
   CU(up(eng->ep_prob, ep_prob));
   CU(cudaStreamSynchronize(s));   // staging vectors go out of scope
 
-  if (eng->max_seg > 16384) return fail(TW_ERR_RANGE_LIMIT, "bind: a service has more than 16384 spans per list (sort limit)");
+  // lists too long for the shared-memory sort of tw_prepare get a slab of global scratch each
+  {
+    std::vector<int32_t> long_seg;
+    int64_t longest = 0;
+    for (int p = 0; p < P; ++p) {
+      const int64_t n = h->prob_in_off[p + 1] - h->prob_in_off[p];
+      if (n > kSortSmemCap) { long_seg.push_back(p); longest = n > longest ? n : longest; }
+    }
+    for (int ep = 0; ep < h->n_ep_total; ++ep) {
+      const int64_t n = h->ep_out_off[ep + 1] - h->ep_out_off[ep];
+      if (n > kSortSmemCap) { long_seg.push_back(P + ep); longest = n > longest ? n : longest; }
+      if (n > eng->max_seg) eng->max_seg = (int)n;
+    }
+    if (longest > (int64_t)1 << 28) return fail(TW_ERR_RANGE_LIMIT, "bind: a list has more than 2^28 spans");
+    eng->n_long = (int)long_seg.size();
+    eng->slab_len = 1;
+    while (eng->slab_len < longest) eng->slab_len <<= 1;
+    CU(eng->alloc(&eng->long_seg, long_seg.size()));
+    CU(eng->alloc(&eng->long_scratch, (size_t)eng->n_long * (size_t)eng->slab_len));
+    if (eng->n_long) {
+      CU(cudaMemcpyAsync(eng->long_seg, long_seg.data(), long_seg.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+      CU(cudaStreamSynchronize(s));
+    }
+  }
   eng->bound = true;
   return TW_OK;
 }
@@ -301,7 +328,8 @@ int tw_prepare(tw_engine* eng, void* stream_) {
   cudaStream_t s = (cudaStream_t)stream_;
   CU(cudaSetDevice(eng->device));
   CU(launch_prev_index(eng->dev, eng->prev_idx, s));
-  CU(launch_sort_ends(eng->dev, eng->in_end_sorted, eng->out_end_sorted, eng->max_seg, eng->err_flag, s));
+  CU(launch_sort_ends(eng->dev, eng->in_end_sorted, eng->out_end_sorted, eng->max_seg, eng->long_seg, eng->n_long,
+                      eng->long_scratch, eng->slab_len, eng->err_flag, s));
   TileList tl{eng->score_tiles, eng->score_tiles + eng->n_tiles, eng->n_tiles, kS3Tile};
   CU(launch_tile_meta(eng->dev, tl, eng->tile_win, s));
   eng->launches += 3;

@@ -58,8 +58,10 @@ cudaError_t launch_score_redo(const tw_batch& b, const tw_params* prm, const tw_
 cudaError_t launch_stitch(const tw_batch& b, const tw_params& prm, const uint8_t* cut,
                           const tw_score_out& spec, const tw_pass_out& out, uint32_t* taken_words, size_t taken_n_words,
                           long long node_limit, int* err_flag, cudaStream_t s);
+constexpr int kSortSmemCap = 16384;               // longest list the shared-memory sort network takes
 cudaError_t launch_sort_ends(const tw_batch& b, int64_t* in_end_sorted, int64_t* out_end_sorted,
-                             int max_seg, int* err_flag, cudaStream_t s);
+                             int max_seg, const int32_t* long_seg, int n_long, int64_t* long_scratch,
+                             int64_t slab_len, int* err_flag, cudaStream_t s);
 cudaError_t launch_params0(const tw_batch& b, const int64_t* in_end_sorted,
                            const int64_t* out_end_sorted, const int64_t* prob_gauss_off,
                            const int32_t* batch_prob, const int32_t* batch_idx, int n_batches_total,

@@ -36,10 +36,7 @@ k_sort_ends(tw_batch b, int64_t* __restrict__ in_end_sorted, int64_t* __restrict
     src = b.out_end + off;
     dst = out_end_sorted + off;
   }
-  if (n > pow2_cap) {
-    if (threadIdx.x == 0) atomicMin(err_flag, (int)TW_ERR_RANGE_LIMIT);
-    return;
-  }
+  if (n > pow2_cap) return;      // long lists are sorted in global memory by k_sort_ends_long
   int m = 1;
   while (m < n) m <<= 1;
   for (int x = threadIdx.x; x < m; x += kSortThreads) a[x] = x < n ? src[x] : INT64_MAX;
@@ -60,17 +57,66 @@ k_sort_ends(tw_batch b, int64_t* __restrict__ in_end_sorted, int64_t* __restrict
   for (int x = threadIdx.x; x < n; x += kSortThreads) dst[x] = a[x];
 }
 
+// Lists longer than the shared-memory network (one service with tens of thousands of spans): the same
+// bitonic network on a power-of-two scratch slab in global memory, one 1024-thread CTA per list.
+// long_seg[k] = segment id as above; slab k starts at scratch + k * slab_len.
+__global__ void __launch_bounds__(1024)
+k_sort_ends_long(tw_batch b, const int32_t* __restrict__ long_seg, int64_t* __restrict__ scratch, int64_t slab_len,
+                 int64_t* __restrict__ in_end_sorted, int64_t* __restrict__ out_end_sorted) {
+  const int seg = long_seg[blockIdx.x];
+  int64_t* a = scratch + (int64_t)blockIdx.x * slab_len;
+  const int64_t* src;
+  int64_t* dst;
+  int n;
+  if (seg < b.n_problems) {
+    int64_t off = b.prob_in_off[seg];
+    n = (int)(b.prob_in_off[seg + 1] - off);
+    src = b.in_end + off;
+    dst = in_end_sorted + off;
+  } else {
+    int ep = seg - b.n_problems;
+    int64_t off = b.ep_out_off[ep];
+    n = (int)(b.ep_out_off[ep + 1] - off);
+    src = b.out_end + off;
+    dst = out_end_sorted + off;
+  }
+  int m = 1;
+  while (m < n) m <<= 1;
+  for (int x = threadIdx.x; x < m; x += blockDim.x) a[x] = x < n ? src[x] : INT64_MAX;
+  __syncthreads();
+  for (int k = 2; k <= m; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int x = threadIdx.x; x < m; x += blockDim.x) {
+        int y = x ^ j;
+        if (y > x) {
+          bool up = (x & k) == 0;
+          int64_t ax = a[x], ay = a[y];
+          if ((ax > ay) == up) { a[x] = ay; a[y] = ax; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int x = threadIdx.x; x < n; x += blockDim.x) dst[x] = a[x];
+}
+
 cudaError_t launch_sort_ends(const tw_batch& b, int64_t* in_end_sorted, int64_t* out_end_sorted,
-                             int max_seg, int* err_flag, cudaStream_t s) {
+                             int max_seg, const int32_t* long_seg, int n_long, int64_t* long_scratch,
+                             int64_t slab_len, int* err_flag, cudaStream_t s) {
   int cap = 1;
-  while (cap < max_seg) cap <<= 1;
+  while (cap < max_seg && cap < kSortSmemCap) cap <<= 1;
   size_t smem = (size_t)cap * sizeof(int64_t);
-  if (smem > 200 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(k_sort_ends, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k_sort_ends<<<b.n_problems + b.n_ep_total, kSortThreads, smem, s>>>(b, in_end_sorted, out_end_sorted, cap,
                                                                        err_flag);
-  return cudaGetLastError();
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (n_long > 0) {
+    k_sort_ends_long<<<n_long, 1024, 0, s>>>(b, long_seg, long_scratch, slab_len, in_end_sorted, out_end_sorted);
+    e = cudaGetLastError();
+  }
+  return e;
 }
 
 // ---------------------------------------------------------------------------------------------
