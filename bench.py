@@ -64,7 +64,7 @@ def parse():
     ap.add_argument("--services", type=int, default=8192, help="services per GPU (weak scaling)")
     ap.add_argument("--spans", type=int, default=100_000_000, help="total spans of the list (strong scaling)")
     ap.add_argument("--n-in", type=int, default=1000, help="incoming spans per service")
-    ap.add_argument("--cpu-sample", type=int, default=384, help="services in the CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=1536, help="services in the CPU-baseline sample")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--seed", type=int, default=10)
     return ap.parse_args()
@@ -303,6 +303,34 @@ def measure(args, blocks, hb, dev_index, steps, warmup, gather=None, rank=0, wor
                 "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": round(score_ms, 4),
                 "tiles_redone_sequentially": eng.redo_tile_count(), "tiles": eng.tile_count()}
+    # ---- FP64 roofline of the refit (27 ms of the step is here): the EM sweeps of k_gmm_bic<K> / k_gmm_final<K>
+    # count their sample-component evaluations (tw_gmm_work); one evaluation is 27 FP64 instructions in
+    # scikit-learn's unfused operation order, 10 of them FMAs = 37 flops; the peak is this
+    # device's measured DFMA rate (tw_measure_fp64_peak, builder-measured, not in MEASURED_PEAKS.json)
+    roofline_refit = None
+    try:
+        dly, cnt = eng.delays(res["assign_pass0"])
+        eng.gmm_refit(dly, cnt, seed_select=args.seed)
+        eng.gmm_work(reset=True)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng.gmm_refit(dly, cnt, seed_select=args.seed)
+        b.record()
+        torch.cuda.synchronize()
+        refit_ms = a.elapsed_time(b)
+        evals = eng.gmm_work(reset=True)
+        peak_tf = eng.fp64_peak_tflops()
+        ach_tf = evals * 37.0 / (refit_ms * 1e-3) / 1e12
+        roofline_refit = {"kernel": "refit: EM sweeps of k_gmm_bic<1..5> + k_gmm_final<K> (whole tw_gmm_refit time as the "
+                                    "denominator, k-means seeding / Lloyd kernels included)",
+                          "bound": "fp64", "achieved": round(ach_tf, 3), "peak": round(peak_tf, 2),
+                          "peak_source": "tw_measure_fp64_peak (builder-measured DFMA rate of this device)",
+                          "unit": "TFLOP/s", "frac": round(ach_tf / peak_tf, 4),
+                          "fp64_issue_frac": round(evals * 27.0 / (refit_ms * 1e-3) / (peak_tf * 1e12 / 2.0), 4),
+                          "em_sample_component_evaluations": int(evals), "flops_per_evaluation": 37,
+                          "fp64_instructions_per_evaluation": 27, "refit_ms": round(refit_ms, 3)}
+    except Exception as ex:       # a measurement aid must not take the line down
+        roofline_refit = {"error": repr(ex)[:200]}
     eng.close()
 
     # ---- leg 2: end to end through the public batch API, host buffers in and out.  The caller's
@@ -335,7 +363,7 @@ def measure(args, blocks, hb, dev_index, steps, warmup, gather=None, rank=0, wor
     if want_cpu and rank == 0 and world == 1:
         cpu = cpu_baseline(blocks, gpu_assign, cpu_sample or args.cpu_sample, args.seed, assign_pass0)
     return dict(n_spans=n_spans, resident_ms=resident_ms, launches=launches, accuracy=acc, unassigned=unassigned,
-                roofline=roofline, e2e=e2e, cpu=cpu, gather_ok=gather_ok,
+                roofline=roofline, roofline_refit=roofline_refit, e2e=e2e, cpu=cpu, gather_ok=gather_ok,
                 clocks=sampler.summary() if sampler else None)
 
 
@@ -515,7 +543,8 @@ def run_ours(args):
                 "op": "all_gather_into_tensor(int32 assign)",
                 "bytes_received_per_rank_per_step": gather.bytes_received_per_rank,
                 "own_shard_round_trips": m["gather_ok"]},
-            "clocks": m["clocks"], "roofline": m["roofline"], "cpu_baseline": m["cpu"], "impl": "ours",
+            "clocks": m["clocks"], "roofline": m["roofline"], "roofline_refit": m["roofline_refit"],
+            "cpu_baseline": m["cpu"], "impl": "ours",
             "extra_workloads": extra,
         }
         print(json.dumps(line))

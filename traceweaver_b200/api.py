@@ -92,7 +92,7 @@ class BatchSolver:
             return [(0, hb.n_problems, hb)]
         # a first group (its host->device copy is the only one nothing can hide), the rest in equal
         # in-span counts
-        first = self.FIRST_GROUP_FRACTION if C == 2 else 1.0 / C
+        first = self.FIRST_GROUP_FRACTION if (C == 2 or self.FIRST_GROUP_FRACTION < 1.0 / C) else 1.0 / C
         fr = first + (1.0 - first) * np.arange(0, C - 1) / max(C - 1, 1)
         cuts = np.searchsorted(hb.prob_in_off, fr * n_in, side="left")
         edges = sorted(set([0, hb.n_problems] + [int(c) for c in cuts if 0 < c < hb.n_problems]))

@@ -57,6 +57,17 @@ def build_profiling():
     return out
 
 
+def build_variant(name, defines):
+    """libtw_b200_<name>.so with extra -D flags: measurement variants (scripts/*), never used by the product."""
+    out = os.path.join(PKG, f"libtw_b200_{name}.so")
+    cmd = [NVCC] + FLAGS + [f"-D{d}" for d in defines] + ["-o", out] + sources()
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        print(res.stdout)
+        raise RuntimeError(f"nvcc failed (variant {name})")
+    return out
+
+
 if __name__ == "__main__":
     if "--prof" in sys.argv:
         print(build_profiling())

@@ -819,7 +819,6 @@ k_gmm_final(FitSel sel, const int64_t* __restrict__ term_sample_off, const doubl
   }
 }
 
-#ifdef TW_PROFILE_PHASES
 // ---- FP64 issue-rate micro-benchmark (the peak the refit's roofline is quoted against): every thread
 // runs 8 independent DFMA chains; 2 flops per DFMA.
 __global__ void __launch_bounds__(256)
@@ -850,6 +849,7 @@ cudaError_t gmm_work_read(unsigned long long* out, bool reset) {
   return e;
 }
 
+#ifdef TW_PROFILE_PHASES
 extern "C" int tw_debug_gmm_phases(unsigned long long* out16, int reset) {
   cudaError_t e = cudaMemcpyFromSymbol(out16, g_gmm_phase, sizeof(unsigned long long) * 16);
   if (e != cudaSuccess) return -2;
