@@ -68,6 +68,11 @@ struct tw_engine {
   uint32_t* skip_taken = nullptr;
   int32_t* skip_win = nullptr;
   int* err_flag = nullptr;
+  int32_t* unit_prob = nullptr;      // stitch units (k_stitch_units)
+  int32_t* unit_lo = nullptr;
+  int32_t* unit_hi = nullptr;
+  int* unit_count = nullptr;
+  int max_units = 0;
   int32_t* long_seg = nullptr;       // lists longer than kSortSmemCap (sorted in global memory)
   int n_long = 0;
   int64_t* long_scratch = nullptr;
@@ -295,6 +300,17 @@ int tw_engine_bind(tw_engine* eng, const tw_batch* dev, const tw_batch* h, void*
   CU(up(eng->ep_prob, ep_prob));
   CU(cudaStreamSynchronize(s));   // staging vectors go out of scope
 
+  // unit list of the stitch kernel: at most n / kStitchUnitMin + 1 units per service
+  {
+    int64_t mu = 0;
+    for (int p = 0; p < P; ++p) mu += (h->prob_in_off[p + 1] - h->prob_in_off[p]) / kStitchUnitMin + 1;
+    if (mu > 0x7fffffff) return fail(TW_ERR_RANGE_LIMIT, "bind: too many stitch units");
+    eng->max_units = (int)mu;
+    CU(eng->alloc(&eng->unit_prob, (size_t)mu));
+    CU(eng->alloc(&eng->unit_lo, (size_t)mu));
+    CU(eng->alloc(&eng->unit_hi, (size_t)mu));
+    CU(eng->alloc(&eng->unit_count, 1));
+  }
   // lists too long for the shared-memory sort of tw_prepare get a slab of global scratch each
   {
     std::vector<int32_t> long_seg;
@@ -630,9 +646,10 @@ int tw_stitch(tw_engine* eng, const tw_params* params, const uint8_t* cut, const
       return fail(TW_ERR_INVALID, "tw_stitch: `undeleted` needs top-K, n_feasible and the used maps");
     spec = *undeleted;
   }
-  CU(launch_stitch(eng->dev, *params, cut, spec, *out, eng->taken, eng->taken_words, eng->node_limit, eng->err_flag,
-                   (cudaStream_t)stream));
-  eng->launches += 1;
+  StitchUnits ub{eng->unit_prob, eng->unit_lo, eng->unit_hi, eng->unit_count};
+  CU(launch_stitch(eng->dev, *params, cut, spec, *out, eng->taken, eng->taken_words, eng->node_limit, ub, eng->max_units,
+                   eng->device, eng->err_flag, (cudaStream_t)stream));
+  eng->launches += undeleted ? 2 : 1;
   return TW_OK;
 }
 

@@ -55,9 +55,18 @@ cudaError_t launch_cut(const tw_batch& b, const tw_score_out& out, const ScoreTi
 cudaError_t launch_score_redo(const tw_batch& b, const tw_params* prm, const tw_score_out& out,
                               const TileList& wide, const int32_t* prev_idx, uint8_t* tile_overflow,
                               int device, int* err_flag, cudaStream_t s);
+// units of the stitch kernel (tw_stitch.cu: k_stitch_units): unit u = in-spans [lo[u], hi[u]) of service prob[u]
+struct StitchUnits {
+  int32_t* prob;
+  int32_t* lo;
+  int32_t* hi;
+  int* count;
+};
+constexpr int kStitchUnitMin = 48;               // a unit is closed at the first strong cut after this many in-spans
 cudaError_t launch_stitch(const tw_batch& b, const tw_params& prm, const uint8_t* cut,
                           const tw_score_out& spec, const tw_pass_out& out, uint32_t* taken_words, size_t taken_n_words,
-                          long long node_limit, int* err_flag, cudaStream_t s);
+                          long long node_limit, const StitchUnits& unit_buf, int max_units, int device, int* err_flag,
+                          cudaStream_t s);
 constexpr int kSortSmemCap = 16384;               // longest list the shared-memory sort network takes
 cudaError_t launch_sort_ends(const tw_batch& b, int64_t* in_end_sorted, int64_t* out_end_sorted,
                              int max_seg, const int32_t* long_seg, int n_long, int64_t* long_scratch,

@@ -552,14 +552,25 @@ __device__ __noinline__ long long stitch_mwis_large(StitchWarpSmem& sm, int E, i
 
 __global__ void __launch_bounds__(kStitchWarps * 32, 10)
 k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_score_out spec, tw_pass_out out,
-         uint32_t* __restrict__ taken, long long node_limit, int* __restrict__ err_flag) {
+         uint32_t* __restrict__ taken, long long node_limit, StitchUnits units, int* __restrict__ err_flag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double etab[64];
   load_exp_table(etab);
   const int warp_in_block = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int p = blockIdx.x * kStitchWarps + warp_in_block;
-  if (p >= b.n_problems) return;
+  // one warp = one UNIT: a stretch [u0, u1) of one service's in-spans that shares no candidate span with
+  // the rest of the service (k_stitch_units), or the whole service when no unit list was built
+  const int u = blockIdx.x * kStitchWarps + warp_in_block;
+  int p, u0 = 0, u1 = -1;
+  if (units.prob) {
+    if (u >= *units.count) return;
+    p = units.prob[u];
+    u0 = units.lo[u];
+    u1 = units.hi[u];
+  } else {
+    p = u;
+    if (p >= b.n_problems) return;
+  }
   StitchWarpSmem& sm = reinterpret_cast<StitchWarpSmem*>(smem_raw)[warp_in_block];
 #ifdef TW_PROFILE_PHASES
   long long _sp_t0 = clock64();
@@ -575,6 +586,7 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
   const ProbView& v = sm.v;
   WindowBuf& wb = sm.wb;
   const int n = v.n_in, E = v.E;
+  if (u1 < 0) u1 = n;
   const uint8_t* cut = cut_all + v.in_off;
 
   // taken bitmap of (problem, ep): word-aligned region, see tw_api.cu (taken_words)
@@ -598,8 +610,10 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
     for (int x = lane; x < tk_words; x += 32) { sm.tk[x] = 0u; sm.tmp[x] = 0u; }
   __syncwarp();
   // defaults
-  for (int i = lane; i < n; i += 32) out.mis_rank[v.in_off + i] = -1;
-  for (int64_t x = lane; x < (int64_t)n * E; x += 32) out.assign[v.tuple_off + x] = -1;
+  for (int i = u0 + lane; i < u1; i += 32) {
+    out.mis_rank[v.in_off + i] = -1;
+    for (int e = 0; e < E; ++e) out.assign[v.tuple_off + (int64_t)e * n + i] = -1;
+  }
 
   const double* gauss_base = prm.mode == TW_PARAMS_GAUSS_BATCHED
                                  ? prm.gauss + prm.prob_gauss_off[p] * TW_GAUSS_REC : nullptr;
@@ -609,7 +623,7 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
   wc.init();
   int not_best = 0, unassigned = 0;
   long long max_nodes = 0;
-  int ws = 0;
+  int ws = u0;
   bool skip_run = false;
   const bool can_run = tk_smem && spec.used_lo != nullptr && out.topk_score == nullptr;
   TW_SPHASE(0);                                  // setup + defaults
@@ -634,9 +648,9 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
       prefetch_l1(cut + ip);
     }
   };
-  prefetch_ahead(0);
-  int prefetched_to = 32;
-  while (ws < n) {
+  prefetch_ahead(u0);
+  int prefetched_to = u0 + 32;
+  while (ws < u1) {
     if (ws + 32 >= prefetched_to) { prefetch_ahead(prefetched_to); prefetched_to += 32; }
     // ---- run of consecutive ONE-in-span windows, one lane each.  Windows only interact through
     // the taken bits, so if (a) every in-span of the run passes the fast-path test against the bits
@@ -648,7 +662,7 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
       // (or it is the last one): at a window start the size cap cannot be the reason (count <= 2).
       // After such a run the cursor's count is irrelevant: the next visit sees cut[] set and resets it.
       const int ij = ws + lane;
-      const bool single = ij < n && (ij == n - 1 ? ij != 0 : cut[ij + 1] != 0);
+      const bool single = ij < u1 && (ij == n - 1 ? ij != 0 : cut[ij + 1] != 0);
       const unsigned sm_mask = __ballot_sync(0xffffffffu, single);
       const int R = sm_mask == 0xffffffffu ? 32 : __ffs(~sm_mask) - 1;
       TW_SPHASE(1);                              // run extent (cut flags)
@@ -836,13 +850,94 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
   }
   if (lane == 0) {
     if (rc != TW_OK) atomicMin(err_flag, rc);
-    if (out.counters) {
-      out.counters[p * 4 + 0] = not_best;
-      out.counters[p * 4 + 1] = unassigned;
-      out.counters[p * 4 + 2] = (int)(max_nodes > 0x7fffffffLL ? 0x7fffffffLL : max_nodes);
-      out.counters[p * 4 + 3] = rc;
+    if (out.counters) {          // zeroed by launch_stitch; several units of one service add up
+      atomicAdd(&out.counters[p * 4 + 0], not_best);
+      atomicAdd(&out.counters[p * 4 + 1], unassigned);
+      atomicMax(&out.counters[p * 4 + 2], (int)(max_nodes > 0x7fffffffLL ? 0x7fffffffLL : max_nodes));
+      atomicMin(&out.counters[p * 4 + 3], rc);
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Units of the stitch: intra-service parallelism.  The hot loop of the reference is one sequential
+// walk per service, but only because deletion couples windows that compete for the same spans.  A
+// perfect cut at in-span i is STRONG when, for every callee, every candidate position of the in-spans
+// before i lies below the first position an in-span from i on can use (lists and in-spans are sorted by
+// start, so that first position, lower_bound(in_i.start), is a lower bound for all later in-spans too).
+// Candidates with deletion are a subset of the candidates on the undeleted lists (the maps of the
+// scoring kernel), so the two sides of a strong cut never read or take the same span: they can be
+// stitched by different warps in any order with the result of the sequential walk.  One warp per
+// service scans its in-spans 32 at a time (exclusive prefix maximum of the highest candidate position
+// per callee) and closes a unit at a strong cut once it holds at least `min_len` in-spans.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_stitch_units(tw_batch b, const uint8_t* __restrict__ cut_all, tw_score_out spec, int min_len, StitchUnits units) {
+  const int p = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (p >= b.n_problems) return;
+  const int ep0 = b.prob_ep_off[p], E = b.prob_ep_off[p + 1] - ep0;
+  const int64_t in_off = b.prob_in_off[p];
+  const int n = (int)(b.prob_in_off[p + 1] - in_off);
+  const int64_t tuple_off = b.prob_tuple_off[p];
+  const uint8_t* cut = cut_all + in_off;
+  int run_max[TW_MAX_E];
+#pragma unroll
+  for (int e = 0; e < TW_MAX_E; ++e) run_max[e] = -1;
+  int unit_start = 0;
+  auto emit = [&](int a, int z) {
+    if (lane == 0) {
+      const int idx = atomicAdd(units.count, 1);
+      units.prob[idx] = p;
+      units.lo[idx] = a;
+      units.hi[idx] = z;
+    }
+  };
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    const bool valid = i < n;
+    bool strong = valid && i >= 1 && cut[i] != 0;
+    const int64_t gi = in_off + i;
+    const bool wide = valid ? spec.used_wide[gi] != 0 : false;
+#pragma unroll
+    for (int e = 0; e < TW_MAX_E; ++e) {
+      if (e >= E) break;
+      int first = 0x7fffffff, hi = -1;
+      if (valid) {
+        const int64_t off = b.ep_out_off[ep0 + e];
+        const int no = (int)(b.ep_out_off[ep0 + e + 1] - off);
+        if (wide) {
+          first = lower_bound(b.out_start + off, no, b.in_start[gi]);
+          hi = upper_bound(b.out_start + off, no, b.in_end[gi]) - 1;
+        } else {
+          const int64_t q = tuple_off + (int64_t)i * E + e;
+          first = spec.used_lo[q];
+          const uint32_t m0 = spec.used_bits[2 * q], m1 = spec.used_bits[2 * q + 1];
+          hi = m1 ? first + 63 - __clz(m1) : m0 ? first + 31 - __clz(m0) : -1;
+        }
+      }
+      // exclusive prefix maximum of hi over the lanes, seeded with the maximum of the earlier chunks
+      int pm = hi;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, pm, d);
+        if (lane >= d) pm = o > pm ? o : pm;
+      }
+      int ex = __shfl_up_sync(0xffffffffu, pm, 1);
+      if (lane == 0) ex = -1;
+      ex = ex > run_max[e] ? ex : run_max[e];
+      if (!(ex < first)) strong = false;
+      const int tot = __shfl_sync(0xffffffffu, pm, 31);
+      run_max[e] = tot > run_max[e] ? tot : run_max[e];
+    }
+    unsigned sm = __ballot_sync(0xffffffffu, strong);
+    while (sm) {
+      const int q = base + __ffs(sm) - 1;
+      sm &= sm - 1u;
+      if (q - unit_start >= min_len) { emit(unit_start, q); unit_start = q; }
+    }
+  }
+  emit(unit_start, n);
 }
 
 #ifdef TW_PROFILE_PHASES
@@ -859,18 +954,34 @@ extern "C" int tw_debug_stitch_phases(unsigned long long* out16, int reset) {
 
 cudaError_t launch_stitch(const tw_batch& b, const tw_params& prm, const uint8_t* cut,
                           const tw_score_out& spec, const tw_pass_out& out, uint32_t* taken_words, size_t taken_n_words,
-                          long long node_limit, int* err_flag, cudaStream_t s) {
+                          long long node_limit, const StitchUnits& unit_buf, int max_units, int device, int* err_flag,
+                          cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(taken_words, 0, taken_n_words * sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
+  if (out.counters) {
+    e = cudaMemsetAsync(out.counters, 0, (size_t)b.n_problems * 4 * sizeof(int32_t), s);
+    if (e != cudaSuccess) return e;
+  }
   size_t smem = sizeof(StitchWarpSmem) * kStitchWarps;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {false};
+  if (device >= 0 && device < 64 && !attr_done[device]) {
     e = cudaFuncSetAttribute(k_stitch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    attr_done[device] = true;
   }
-  int blocks = (b.n_problems + kStitchWarps - 1) / kStitchWarps;
-  k_stitch<<<blocks, kStitchWarps * 32, smem, s>>>(b, prm, cut, spec, out, taken_words, node_limit, err_flag);
+  StitchUnits units{nullptr, nullptr, nullptr, nullptr};
+  int warps = b.n_problems;
+  if (spec.used_lo && unit_buf.prob && max_units > 0) {      // the maps prove which cuts are strong
+    units = unit_buf;
+    e = cudaMemsetAsync(units.count, 0, sizeof(int), s);
+    if (e != cudaSuccess) return e;
+    k_stitch_units<<<(b.n_problems + 3) / 4, 128, 0, s>>>(b, cut, spec, kStitchUnitMin, units);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    warps = max_units;
+  }
+  int blocks = (warps + kStitchWarps - 1) / kStitchWarps;
+  k_stitch<<<blocks, kStitchWarps * 32, smem, s>>>(b, prm, cut, spec, out, taken_words, node_limit, units, err_flag);
   return cudaGetLastError();
 }
 
