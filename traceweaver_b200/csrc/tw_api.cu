@@ -649,7 +649,7 @@ int tw_stitch(tw_engine* eng, const tw_params* params, const uint8_t* cut, const
   StitchUnits ub{eng->unit_prob, eng->unit_lo, eng->unit_hi, eng->unit_count};
   CU(launch_stitch(eng->dev, *params, cut, spec, *out, eng->taken, eng->taken_words, eng->node_limit, ub, eng->max_units,
                    eng->device, eng->err_flag, (cudaStream_t)stream));
-  eng->launches += undeleted ? 2 : 1;
+  eng->launches += (undeleted && eng->dev.n_problems < kStitchUnitMaxServices) ? 2 : 1;
   return TW_OK;
 }
 

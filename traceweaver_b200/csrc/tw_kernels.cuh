@@ -63,6 +63,7 @@ struct StitchUnits {
   int* count;
 };
 constexpr int kStitchUnitMin = 48;               // a unit is closed at the first strong cut after this many in-spans
+constexpr int kStitchUnitMaxServices = 4096;     // batches with at least this many services keep one warp per service
 cudaError_t launch_stitch(const tw_batch& b, const tw_params& prm, const uint8_t* cut,
                           const tw_score_out& spec, const tw_pass_out& out, uint32_t* taken_words, size_t taken_n_words,
                           long long node_limit, const StitchUnits& unit_buf, int max_units, int device, int* err_flag,

@@ -971,7 +971,11 @@ cudaError_t launch_stitch(const tw_batch& b, const tw_params& prm, const uint8_t
   }
   StitchUnits units{nullptr, nullptr, nullptr, nullptr};
   int warps = b.n_problems;
-  if (spec.used_lo && unit_buf.prob && max_units > 0) {      // the maps prove which cuts are strong
+  // Units pay when services alone cannot fill the machine (a shipped directory has 2-6 services; 148 SMs
+  // hold ~2700 stitch warps); with thousands of services one warp per service is already enough
+  // parallelism and the unit pre-pass + per-unit set-up cost more than the shorter tail gains
+  // (8192 services: 9.6 vs 8.7 ms per pass).  The maps of the scoring kernel prove which cuts are strong.
+  if (spec.used_lo && unit_buf.prob && max_units > 0 && b.n_problems < kStitchUnitMaxServices) {
     units = unit_buf;
     e = cudaMemsetAsync(units.count, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
