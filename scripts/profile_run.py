@@ -8,7 +8,11 @@ from traceweaver_b200.batch import build_batch_from_blocks
 from traceweaver_b200.engine import Engine
 from traceweaver_b200.predictor import solve_bound
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-blocks = synth.hotel_stream(S, 1000, seed=10)
+if len(sys.argv) > 2:      # bench.py's streams: "media" / "alibaba" / "hotel"
+    from traceweaver_b200 import shard
+    blocks = shard.generate_slice(shard.stream_spec(sys.argv[2], S, 1000, 10), 0, S)
+else:
+    blocks = synth.hotel_stream(S, 1000, seed=10)
 hb = build_batch_from_blocks(blocks)
 eng = Engine(0)
 eng.bind(hb)

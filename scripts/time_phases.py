@@ -12,7 +12,14 @@ from traceweaver_b200.engine import Engine
 
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 n_in = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
-t0 = time.time(); blocks = synth.hotel_stream(S, n_in, seed=10); hb = build_batch_from_blocks(blocks)
+wl = sys.argv[3] if len(sys.argv) > 3 else None          # "media" / "alibaba" / "hotel": bench.py's streams
+t0 = time.time()
+if wl:
+    from traceweaver_b200 import shard
+    blocks = shard.generate_slice(shard.stream_spec(wl, S, n_in, 10), 0, S)
+else:
+    blocks = synth.hotel_stream(S, n_in, seed=10)
+hb = build_batch_from_blocks(blocks)
 nsp = synth.span_count(blocks); print(f"{hb.n_problems} services, {nsp/1e6:.2f} M spans, gen {time.time()-t0:.1f}s")
 eng = Engine(0)
 t0 = time.time(); eng.bind(hb); torch.cuda.synchronize(); print(f"bind+upload {time.time()-t0:.3f}s")

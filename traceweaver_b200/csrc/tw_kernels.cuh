@@ -13,6 +13,7 @@ constexpr int kS3Tile = 128;                     // in-spans per tile
 constexpr int kStageSpans = 1536;                // out spans staged in shared memory per tile
 constexpr int kTblCap = 3072;                    // term-table slots per CTA round (tw_core.cuh)
 constexpr int kWarpTblCap = 256;                 // term-table slots per stitch warp (search path only)
+constexpr int kRedoCoopCombos = 256;             // redo kernel: in-spans with more combinations are scored by the whole warp
 constexpr int kStitchCoopCombos = 512;           // in-spans with more candidate combinations are searched by the whole warp
 constexpr int kTakenWords = 256;                 // taken-bitmap words a stitch warp keeps in shared memory
 constexpr int kNarrowW = 2;                      // bitmap words per (in-span, ep): 64 candidates

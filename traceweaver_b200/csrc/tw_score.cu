@@ -239,6 +239,98 @@ __device__ __forceinline__ void score_tile(const tw_batch& b, const tw_params& p
   if (has_params) {
     bool pending = do_score;
     const int lane = tid & 31, wid = tid >> 5;
+    // ---- heavy in-spans, one at a time by the WHOLE warp (one-warp CTAs only: the redo kernel).  A thread
+    // that walks thousands of tuples alone keeps one lane of 32 busy and sets the kernel's time; here the
+    // owner lays out its term tables, all lanes evaluate the slots, then take the combinations lane,
+    // lane + 32, ... (ascending combination index = depth-first leaf order), mark the candidate maps, keep
+    // their own top K, and the warp merges the heads.  Two equal scores among the best -> the reference's
+    // heap order decides (topk_offer): the in-span stays pending and its owner redoes it alone below.
+    if (T == 32) {
+      const long long Pown = pending ? combo_count(v, r) : 0;
+      unsigned heavy = __ballot_sync(0xffffffffu, pending && tsize <= kTblCap && Pown > kRedoCoopCombos &&
+                                                      Pown < (1LL << 31));
+      const int brel_own = i / TW_PARAM_BATCH - batch0;
+      while (heavy) {
+        const int L = __ffs(heavy) - 1;
+        heavy &= heavy - 1u;
+        int lo_b[TW_MAX_E], r_b[TW_MAX_E], o_last_b[TW_MAX_E], lo_abs_b[TW_MAX_E];
+        for (int e = 0; e < E; ++e) {
+          lo_b[e] = __shfl_sync(0xffffffffu, lo[e], L);
+          r_b[e] = __shfl_sync(0xffffffffu, r[e], L);
+          lo_abs_b[e] = sm.lo_abs[L][e];
+        }
+        const int tsz = __shfl_sync(0xffffffffu, tsize, L);
+        const long long P_b = __shfl_sync(0xffffffffu, Pown, L);
+        term_table_last_offsets(v, r_b, o_last_b);
+        if (lane == L)
+          term_table_fill(v, in_s, in_e, w, lo, r, o_last_b, brel_own, [](int, int) { return false; }, sm.tbl, sm.sid);
+        __syncwarp();
+        for (int sl = lane; sl < tsz; sl += 32) {
+          const uint8_t id = sm.sid[sl];
+          if (id != TW_SLOT_INVALID) {
+            ParamView pv;
+            pv.mode = prm.mode;
+            pv.gauss = sm.prm + (id >> 6) * v.n_terms * TW_GAUSS_REC;
+            pv.mix = sm.prm;
+            pv.etab = sm.etab;
+            sm.tbl[sl] = term_logpdf(pv, id & 63, sm.tbl[sl]);
+          }
+        }
+        __syncwarp();
+        TopK part;
+        part.clear();
+        int leaves = 0;
+        bool tie = false, ovf = false;
+        enumerate_combos(v, sm.win, lo_b, r_b, o_last_b, sm.sid, lane, 32, P_b,
+                         [&](const int* c, const int64_t* ce, long long) {
+                           ++leaves;
+                           for (int e = 0; e < E; ++e) {
+                             const int bit = c[e] - lo_abs_b[e];
+                             if (bit >= 32 * W) ovf = true;
+                             else atomicOr(&sm.used[L][e][bit >> 5], 1u << (bit & 31));
+                           }
+                           const double sc = table_score(v, r_b, lo_abs_b, sm.tbl, c, ce);
+                           for (int k = 0; k < part.n; ++k) tie = tie || part.score[k] == sc;
+                           tie = tie || sc != sc;
+                           topk_offer_sorted(v, part, sc, c);
+                         });
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) leaves += __shfl_xor_sync(0xffffffffu, leaves, d);
+        if (ovf) sm.overflow = 1;
+        TopK tkc;
+        tkc.clear();
+        int head = 0;
+        double prev = 0.0;
+        for (int round = 0; round <= TW_K; ++round) {
+          const double hs = head < part.n ? part.score[head] : -INFINITY;
+          double mx = hs;
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) {
+            const double o = __shfl_xor_sync(0xffffffffu, mx, d);
+            mx = o > mx ? o : mx;
+          }
+          if (!(mx > -INFINITY)) break;
+          const unsigned who = __ballot_sync(0xffffffffu, hs == mx);
+          if (__popc(who) > 1 || (round > 0 && mx == prev)) tie = true;
+          prev = mx;
+          const int wl = __ffs(who) - 1;
+          if (round < TW_K) {
+            for (int e = 0; e < E; ++e) {
+              const int ci = __shfl_sync(0xffffffffu, head < part.n ? part.idx[head][e] : -1, wl);
+              if (lane == L) tkc.idx[round][e] = ci;
+            }
+            if (lane == L) { tkc.score[round] = mx; tkc.n = round + 1; }
+          }
+          if (lane == wl) ++head;
+        }
+        tie = __any_sync(0xffffffffu, tie);
+        if (!tie && lane == L) {
+          write_out(tkc, leaves);
+          pending = false;
+        }
+        __syncwarp();
+      }
+    }
     while (true) {
       // exclusive prefix of the pending threads' table sizes
       int my = pending ? tsize : 0, incl = my;
