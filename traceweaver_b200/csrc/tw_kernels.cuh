@@ -12,7 +12,10 @@ constexpr int kS3Threads = 128;                  // tw_score3.cu: one CTA = one 
 constexpr int kS3Tile = 128;                     // in-spans per tile
 constexpr int kStageSpans = 1536;                // out spans staged in shared memory per tile
 constexpr int kTblCap = 3072;                    // term-table slots per CTA round (tw_core.cuh)
-constexpr int kWarpTblCap = 256;                 // term-table slots per stitch warp (search path only)
+#ifndef TW_WARP_TBL_CAP
+#define TW_WARP_TBL_CAP 256
+#endif
+constexpr int kWarpTblCap = TW_WARP_TBL_CAP;     // term-table slots per stitch warp (search path only)
 constexpr int kRedoCoopCombos = 256;             // redo kernel: in-spans with more combinations are scored by the whole warp
 constexpr int kStitchCoopCombos = 512;           // in-spans with more candidate combinations are searched by the whole warp
 constexpr int kTakenWords = 256;                 // taken-bitmap words a stitch warp keeps in shared memory
