@@ -434,6 +434,56 @@ def shipped_directories(dev_index):
             "reference_python_seconds_when_minted": round(ref_s, 1), "per_directory": rows}
 
 
+def cache_mode_fixtures(dev_index):
+    """the services of the reference's cache-mode runs (exps/exp2: hotel `frontend` with
+    --cache_rate 5..50 %, tests/golden_cache) through the skip regime of the engine (tw_skip_solve), each
+    compared with the assignments the reference returned."""
+    import glob
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from golden_util import Golden
+    from traceweaver_b200 import skipmode
+    from traceweaver_b200.engine import Engine
+    files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden_cache", "*__*.npz")))
+    rows, equal_all, ref_s, tot_ms, tot_spans = [], True, 0.0, 0.0, 0
+    eng = Engine(dev_index)
+    for f in files:
+        g = Golden(f)
+        if not any(v != 0 for v in g.meta["skip_budget"].values()):
+            continue
+        prob = g.problem()
+        labels = [g.meta["in_ep"]] + g.topo
+        wins = [tuple(w) for w in g.meta["time_windows_before"]]
+
+        def once():
+            st = skipmode.SkipState()
+            st.time_windows = list(wins)
+            return skipmode.solve(eng, prob.in_start, prob.in_end, prob.out_start, prob.out_end, prob.preds,
+                                  labels=labels, state=st, want_topk=False)
+        once()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = once()
+        ms = (time.perf_counter() - t0) * 1e3
+        ok = bool(np.array_equal(res["assign"], g.z["assign"]))
+        equal_all = equal_all and ok
+        spans = int(prob.n_in + sum(len(o) for o in prob.out_start))
+        rows.append({"fixture": os.path.basename(f)[:-4], "spans": spans, "ms": round(ms, 2),
+                     "skip_assignments": int((res["assign"] == -2).sum()), "assignments_equal_reference": ok,
+                     "reference_python_seconds": round(float(g.meta.get("reference_seconds", 0.0)), 1)})
+        ref_s += float(g.meta.get("reference_seconds", 0.0))
+        tot_ms += ms
+        tot_spans += spans
+    eng.close()
+    if not rows:
+        return None
+    return {"workload": "cache-mode services (skip budgets, exps/exp2 shape): hotel `frontend` fixtures minted from the "
+                        "reference with --cache_rate, one service per call through skipmode.solve (host arrays in and out)",
+            "services": len(rows), "spans": tot_spans, "ms_total": round(tot_ms, 2),
+            "e2e_value": tot_spans / (tot_ms * 1e-3), "unit": UNIT, "assignments_equal_reference": equal_all,
+            "reference_python_seconds_when_minted": round(ref_s, 1), "per_service": rows}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -511,6 +561,12 @@ def run_ours(args):
                 extra.append(sd)
         except Exception as ex:
             extra.append({"workload": "shipped Jaeger directories", "error": repr(ex)[:300]})
+        try:
+            cm = cache_mode_fixtures(local_rank)
+            if cm:
+                extra.append(cm)
+        except Exception as ex:
+            extra.append({"workload": "cache-mode services", "error": repr(ex)[:300]})
 
     if rank == 0:
         K = args.steps

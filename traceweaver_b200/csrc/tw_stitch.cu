@@ -808,8 +808,9 @@ k_stitch(tw_batch b, tw_params prm, const uint8_t* __restrict__ cut_all, tw_scor
     }
     TW_SPHASE(5);                                // fast test + adopt
     // ---- slow path (kept out of line: the hot loop above and below stays small in the instruction cache)
-    TW_SCOUNT(14, __popc(__ballot_sync(0xffffffffu, active && !fast)));
-    if (__any_sync(0xffffffffu, active && !fast))
+    const unsigned slow_mask = __ballot_sync(0xffffffffu, active && !fast);   // (all lanes vote: the counter macro runs on lane 0 only)
+    TW_SCOUNT(14, __popc(slow_mask));
+    if (slow_mask)
       stitch_search_lanes(sm, prm, out, tk_base, w, gauss_base, mix_base, etab, E, lane, ws, i, in_s, in_e,
                           active && !fast, batch0);
     __syncwarp();
