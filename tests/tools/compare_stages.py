@@ -4,7 +4,7 @@ Usage: python scripts/compare_stages.py {hotel,media,alibaba} [services] [n_in] 
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 
@@ -18,7 +18,7 @@ ns = int(sys.argv[2]) if len(sys.argv) > 2 else 2046
 n_in = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
 per = int(sys.argv[4]) if len(sys.argv) > 4 else 2
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from bench import sample_blocks  # noqa: E402
 
 sp = shard.stream_spec(wl, ns, n_in, 10)
