@@ -59,6 +59,9 @@ DATASETS = {
     **{f"hotel_load{l}": (f"data/hotel_reservation/hotel_load{l}", 2) for l in (25, 50, 75, 100, 125, 150)},
     **{f"media_load{l}": (f"data/media_microservices/media_load{l}", 1) for l in (25, 50, 75, 100, 125, 150)},
     **{f"node_load{l}": (f"data/nodejs_microservices/node_load{l}", 0) for l in (25, 50, 75, 100, 125, 150)},
+    # the Alibaba JSON layout (--fix 5) on synthetic traces of that layout (tests/golden/make_alibaba_traces.py;
+    # the real trace is a Git LFS pointer): absolute path, not under /root/reference
+    "alibaba_synth": (os.path.join(HERE, "alibaba_synth"), 5),
 }
 
 
@@ -426,7 +429,7 @@ def run_dataset(name, outdir, v3mod, recorder):
     rel, fix = DATASETS[name]
     scratch = tempfile.mkdtemp(prefix="tw_golden_")
     data = os.path.join(scratch, name)
-    shutil.copytree(os.path.join(REF, rel), data)
+    shutil.copytree(rel if os.path.isabs(rel) else os.path.join(REF, rel), data)
     cache = os.path.join(data, "time_order_filenames.pickle")
     if os.path.exists(cache):
         os.remove(cache)

@@ -24,6 +24,7 @@ REF_DATA = os.path.join(REF_ROOT, "hotel_reservation")
 GOLDENS = sorted(glob.glob(os.path.join(HERE, "golden", "hotel_load*__*.npz")) +
                  glob.glob(os.path.join(HERE, "golden", "media_load*__*.npz")) +
                  glob.glob(os.path.join(HERE, "golden", "node_load*__*.npz")))
+ALIBABA = sorted(glob.glob(os.path.join(HERE, "golden", "alibaba_synth__*.npz")))
 _cache = {}
 
 
@@ -34,6 +35,38 @@ def _services(dataset):
         sub = {"hotel": "hotel_reservation", "media": "media_microservices", "node": "nodejs_microservices"}[layout]
         _cache[dataset] = {s.name: s for s in load_jaeger_dir(os.path.join(REF_ROOT, sub, dataset), layout=layout)}
     return _cache[dataset]
+
+
+def _loopless(name):
+    """The reference names a self-loop service with a random id ("<16 random characters>-loop",
+    executor.py:396-398), the loader with "<callee>-<n>-loop": compare them as one token."""
+    return "<loop>" if name.endswith("-loop") else name
+
+
+@pytest.mark.parametrize("path", ALIBABA, ids=[os.path.basename(p)[:-4] for p in ALIBABA])
+def test_alibaba_layout_matches_reference_loader(path):
+    """`--fix 5` (executor.py:377-470) on the committed synthetic traces of the Alibaba ETL's layout
+    (tests/golden/make_alibaba_traces.py; fixtures minted by the reference run with --fix 5)."""
+    from traceweaver_b200.loader import load_jaeger_dir
+    if "alibaba" not in _cache:
+        _cache["alibaba"] = {_loopless(s.name): s for s in
+                             load_jaeger_dir(os.path.join(HERE, "golden", "alibaba_synth"), layout="alibaba")}
+    g = Golden(path)
+    z, m = g.z, g.meta
+    svc = _cache["alibaba"][_loopless(m["process"])]
+    assert _loopless(svc.in_ep) == _loopless(m["in_ep"])
+    assert [_loopless(e) for e in svc.out_eps_given] == [_loopless(e) for e in m["out_eps_given"]]
+    assert [_loopless(e) for e in svc.out_eps] == [_loopless(e) for e in m["out_eps_topo"]]
+    assert [[_loopless(a), _loopless(b)] for a, b in svc.graph_edges] == [[_loopless(a), _loopless(b)] for a, b in m["graph_edges"]]
+    want, got = g.problem(), svc.problem
+    assert np.array_equal(got.in_start, want.in_start) and np.array_equal(got.in_end, want.in_end)
+    assert got.preds == want.preds
+    for e in range(g.E):
+        assert np.array_equal(got.out_start[e], want.out_start[e]) and np.array_equal(got.out_end[e], want.out_end[e])
+    assert [t for t, _ in svc.in_ids] == list(z["in_trace"]) and [s for _, s in svc.in_ids] == list(z["in_sid"])
+    for e, gidx in enumerate(g.pos_given):
+        assert [s for _, s in svc.out_ids[e]] == list(z[f"out{gidx}_sid"])
+    assert np.array_equal(svc.truth, z["truth"])
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_DATA), reason="reference trace directories not mounted")

@@ -145,6 +145,66 @@ def _nodes_node(d, path):
     return nodes + twins
 
 
+def _nodes_alibaba(d, path, loop_map):
+    """The `--fix 5` reading of traces in the Alibaba ETL's layout (ParseSpansJson with first_span None,
+    executor.py:377-470): every rpc is a server record (processID = callee) plus a client twin with the SAME
+    spanID (processID = caller); there is no `processes` table (ParseProcessesJson2: the processID is the
+    service).  The client twin's id gets the suffix ".client" and becomes the parent of its server record;
+    an rpc whose caller equals its callee (a self loop) has its callee renamed to a fresh "...-loop" service —
+    the reference draws a random name per RPC ID (`selfLoopMap` is keyed by the sanitised span id and lives
+    across traces, executor.py:392-402); here the name is "<callee>-<n>-loop" — and every client span below
+    a span whose rpc id is in that map is moved to its parent's service (executor.py:447-466).  A trace in
+    which some child is not contained in its parent is dropped (executor.py:425-441): returns None."""
+    spans = d["spans"]
+    nodes, key_of = [], {}
+    for s in spans:
+        kind = _span_kind(s)
+        sid = s["spanID"]
+        refs = [r["spanID"] for r in s["references"]]
+        if len(refs) > 1:
+            raise ValueError(f"{path}: span with several references (spans.py:41)")
+        if kind == "client":
+            sid = sid + ".client"
+        elif kind == "server" and len(refs) == 1:
+            refs[0] = sid + ".client"
+        service = s["processID"]
+        if s["caller"] == s["callee"]:
+            rpc = sid[:-7] if sid.endswith(".client") else sid
+            if rpc not in loop_map:
+                loop_map[rpc] = f"{s['callee']}-{len(loop_map)}-loop"
+            if kind == "server":
+                service = loop_map[rpc]
+        key_of[sid] = len(nodes)
+        nodes.append([s["traceID"], sid, s["startTime"], s["duration"], s.get("requestType", s.get("operationName")),
+                      service, kind, refs[0] if refs else None])
+    children = [[] for _ in nodes]
+    for k, nd in enumerate(nodes):
+        par = nd[7]
+        nd[7] = key_of.get(par, -1) if par is not None else -1
+        if par is not None and par in key_of:
+            children[key_of[par]].append(k)
+    root = next((k for k, nd in enumerate(nodes) if nd[7] < 0 and not spans[k]["references"]), None)
+    if root is not None:
+        stack = [root]
+        while stack:                                     # check_time_constraints, executor.py:425-438
+            k = stack.pop()
+            for c in children[k]:
+                if not (nodes[k][2] <= nodes[c][2] and nodes[k][2] + nodes[k][3] >= nodes[c][2] + nodes[c][3]):
+                    return None
+                stack.append(c)
+        stack = [(root, False)]
+        while stack:                                     # traverse_and_update / update_references, :447-466
+            k, below_loop = stack.pop()
+            sid = nodes[k][1]
+            rpc = sid[:-7] if sid.endswith(".client") else sid
+            below = below_loop or rpc in loop_map
+            for c in children[k]:
+                if below and nodes[c][6] == "client":
+                    nodes[c][5] = nodes[k][5]
+                stack.append((c, below))
+    return nodes
+
+
 def _nodes_media(d, path):
     """FixSpans2 (executor.py:539-640), the `--fix 1` rewrite of media_microservices traces, whose
     spans carry no span.kind: the "ComposeReview" span becomes the root (its ancestors are dropped,
@@ -210,8 +270,11 @@ def load_jaeger_dir(directory: str, first_span: Optional[str] = HOTEL_FIRST_SPAN
     on the device in one batch (row f-2); None -> NumPy on the host (same result).
     layout "hotel": spans as recorded (`--fix 2`); "media": FixSpans2 rewrite (`--fix 1`, first span
     "ComposeReview"); "node": FixSpans rewrite (`--fix 0`, first span "init-span")."""
-    if layout not in ("hotel", "media", "node"):
-        raise ValueError(f"layout {layout!r}: only the hotel (--fix 2), media (--fix 1) and node (--fix 0) layouts are built")
+    if layout not in ("hotel", "media", "node", "alibaba"):
+        raise ValueError(f"layout {layout!r}: hotel (--fix 2), media (--fix 1), node (--fix 0) and alibaba (--fix 5) are built")
+    if layout == "alibaba":
+        first_span = None                                # every rooted trace is taken (executor.py:765)
+    loop_map: Dict[str, str] = {}
     if layout == "media":
         first_span = MEDIA_FIRST_SPAN
     if layout == "node":
@@ -232,7 +295,12 @@ def load_jaeger_dir(directory: str, first_span: Optional[str] = HOTEL_FIRST_SPAN
                 accepted.append(d)
         if len(accepted) != 1:
             raise ValueError(f"{path}: expected exactly one rooted trace (executor.py:790)")
-        nodes = {"media": _nodes_media, "node": _nodes_node, "hotel": _nodes_plain}[layout](accepted[0], path)
+        if layout == "alibaba":
+            nodes = _nodes_alibaba(accepted[0], path, loop_map)
+            if nodes is None:
+                continue                                 # time constraint violated: the trace is skipped (:869-871)
+        else:
+            nodes = {"media": _nodes_media, "node": _nodes_node, "hotel": _nodes_plain}[layout](accepted[0], path)
         children: List[List[int]] = [[] for _ in nodes]
         root = None
         for k, node in enumerate(nodes):
