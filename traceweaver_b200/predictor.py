@@ -75,6 +75,7 @@ class TraceWeaverV3:
         # (time_windows, distribution_values: traceweaver_v3.py:40,45 are never reset)
         self.skip_state = skipmode.SkipState()
         self.carry_state = carry_state
+        self._pending_dist = []
 
     # -- marshalling -------------------------------------------------------------------------------
     @staticmethod
@@ -130,12 +131,12 @@ class TraceWeaverV3:
 
         if self.carry_state:
             # the reference runs TallySkipSpans and BuildDistributions for EVERY service (v3:1136, :1149);
-            # in this regime they only leave state behind for a later service with skip budgets
-            labels = [in_ep] + out_eps
-            st = self.skip_state
-            st.time_windows.extend(skipmode.new_time_windows(prob.in_start, prob.in_end))
-            skipmode.build_distributions(self.engine, prob.in_start, prob.in_end, prob.out_start, prob.out_end,
-                                         labels, st)
+            # in this regime they only leave state behind for a later service with skip budgets: the time
+            # windows are appended now (a few tuples), the distribution samples are derived lazily — the
+            # arrays are parked and run through tw_build_dist_samples, in call order, when a service with
+            # skip budgets actually arrives (_find_assignments_skip)
+            self.skip_state.time_windows.extend(skipmode.new_time_windows(prob.in_start, prob.in_end))
+            self._pending_dist.append((prob.in_start, prob.in_end, prob.out_start, prob.out_end, [in_ep] + out_eps))
         dev = self.engine.device
         res = solve_batch(self.engine, hb, seed_select=self.seed_select,
                           truth_assign=torch.from_numpy(truth.reshape(-1)).to(dev),
@@ -174,6 +175,9 @@ class TraceWeaverV3:
         outs = [self._arrays(out_span_partitions[ep]) for ep in out_eps]     # the caller's list order
         preds = [[pos[b] for b, _ in invocation_graph.in_edges(ep)] for ep in out_eps]
         state = self.skip_state if self.carry_state else skipmode.SkipState()
+        for a in self._pending_dist:                  # BuildDistributions of the earlier services, in call order
+            skipmode.build_distributions(self.engine, *a[:4], a[4], state)
+        self._pending_dist = []
         res = skipmode.solve(self.engine, in_s, in_e, [o[0] for o in outs], [o[1] for o in outs], preds,
                              labels=[in_ep] + out_eps, state=state, want_topk=False)
         self.last = res
