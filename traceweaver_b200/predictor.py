@@ -80,7 +80,13 @@ class TraceWeaverV3:
     # -- marshalling -------------------------------------------------------------------------------
     @staticmethod
     def _arrays(spans):
-        s = np.fromiter((sp.start_mus for sp in spans), np.int64, len(spans))
+        raw = [sp.start_mus for sp in spans]
+        if any(isinstance(x, float) and x != int(x) for x in raw):
+            # executor.py --compress_factor > 1 (transforms.repeat_change_spans) divides the start times: float
+            # microseconds, which the engine's int64 timestamps cannot hold — loud, not truncated
+            raise NotImplementedError("fractional start_mus (time-compressed spans): outside the engine's int64 "
+                                      "timestamp model; use the reference for --compress_factor > 1")
+        s = np.fromiter((int(x) for x in raw), np.int64, len(spans))
         d = np.fromiter((sp.duration_mus for sp in spans), np.int64, len(spans))
         return s, s + d
 
