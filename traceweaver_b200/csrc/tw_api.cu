@@ -55,6 +55,7 @@ struct tw_engine {
   uint8_t* own_used_wide = nullptr;
   uint32_t* taken = nullptr;
   size_t taken_words = 0;
+  double* fp64_sink = nullptr;       // tw_measure_fp64_peak
   // ground truth / order / accuracy scratch (tw_truth.cu)
   int32_t* truth_tab = nullptr;
   int64_t* truth_tab_off = nullptr;
@@ -457,8 +458,8 @@ int tw_measure_fp64_peak(tw_engine* eng, double* tflops_out, void* stream_) {
   CU(cudaSetDevice(eng->device));
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, eng->device));
-  double* sink = nullptr;
-  CU(eng->alloc(&sink, 1));
+  CU(eng->alloc(&eng->fp64_sink, 1));
+  double* sink = eng->fp64_sink;
   const int blocks = prop.multiProcessorCount * 8, iters = 1 << 15;
   cudaEvent_t a, b;
   CU(cudaEventCreate(&a));
